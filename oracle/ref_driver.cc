@@ -1,0 +1,253 @@
+/* oracle/ref_driver.cc -- TEST INFRASTRUCTURE ONLY.  Never linked into the product.
+ *
+ * Builds the REFERENCE's own code, in place, from /root/reference (nothing is copied into
+ * this repository): testmaster.cc (which textually includes masterloop.cc and every
+ * header on the path) plus master.cc and stype.cc, against oracle/shim/.  This file adds
+ * a main() around them that
+ *
+ *   unit                         runs the reference's three assert tests
+ *                                (testmaster.cc:295-426; they are commented out of its main)
+ *   chain  SAMPLER ...           runs the reference JobTree + run_master + MasterTester<S>
+ *                                (testmaster.cc:57-293) for L levels and prints every chain
+ *                                row the reference would print (master.cc:347-355), at full
+ *                                precision, with the raw theta bytes
+ *   normal-eval IN OUT           NormalSampler<2>::load/prepare/evaluate_many
+ *                                (normalsampler.hh:66-165) over a binary dataset
+ *   boltz-eval  IN OUT           BoltzmannSampler::evaluate_many (boltzmannsampler.hh:71-82)
+ *   normal-bench N B REPS        times evaluate_many for B nodes (CPU baseline, kind
+ *                                "reference", one thread per node like one MPI worker per node)
+ *   data N                       prints the first values of the normal.cc:41-46 dataset
+ *
+ * Output of `chain` is the golden-vector format of tests/golden/chain_*.tsv:
+ *   depth <TAB> accept <TAB> metric_sum(%.17g) <TAB> theta(hex bytes) <TAB> unparse(theta)
+ */
+#define main testmaster_reference_main
+#include "testmaster.cc"
+#undef main
+
+#include <chrono>
+#include <thread>
+#include <vector>
+
+namespace {
+
+std::string hex(const std::string& s) {
+    static const char* d = "0123456789abcdef";
+    std::string out;
+    for (unsigned char c : s) {
+        out += d[c >> 4];
+        out += d[c & 15];
+    }
+    return out;
+}
+
+size_t g_stop_depth = 0;
+
+/* A completion hook (stype.hh:37-39) that prints what the reference passes to notify()
+ * (master.cc:347-355) without the wall-clock column, then ends the process once the
+ * requested depth has been emitted (testmaster never exits on its own). */
+template <typename T>
+class GoldenHook : public SamplerType {
+  public:
+    std::string unparse(const std::string& theta) const { return load_unparse_theta<T>(theta); }
+    void notify(const JobTree&, size_t depth, const double metric_sum, const std::string& theta,
+                bool accept) {
+        printf("%zu\t%d\t%.17g\t%s\t%s\n", depth, (int) accept, metric_sum, hex(theta).c_str(),
+               unparse(theta).c_str());
+        if (depth >= g_stop_depth) {
+            fflush(stdout);
+            exit(0);
+        }
+    }
+};
+
+double* normal_dataset(size_t n) {
+    /* recipe of samplers/normal.cc:41-46 == testmaster.cc:487-492 */
+    boost::random::mt19937 engine;
+    boost::random::normal_distribution<> dist;
+    double* data = new double[n * 2];
+    for (size_t i = 0; i != n * 2; ++i)
+        data[i] = dist(engine) + (i % 2 ? 100 : 200);
+    return data;
+}
+
+int cmd_chain(int argc, char** argv) {
+    const char* sampler_name = "normal";
+    size_t cores = 9, data_size = 10000, batch_size = 1000, levels = 20, policy = PREDICTIVE,
+           dimension = 1;
+    double reassign_ratio = 1.1, correlation = 0.99;
+    bool threshold = false;
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
+        if (a == "-n") cores = strtoull(next(), 0, 0);
+        else if (a == "-d") data_size = strtoull(next(), 0, 0);
+        else if (a == "-b") batch_size = strtoull(next(), 0, 0);
+        else if (a == "-l") levels = strtoull(next(), 0, 0);
+        else if (a == "-s") policy = strtoull(next(), 0, 0);
+        else if (a == "-D") dimension = strtoull(next(), 0, 0);
+        else if (a == "-r") reassign_ratio = strtod(next(), 0);
+        else if (a == "-c") correlation = strtod(next(), 0);
+        else if (a == "-t") threshold = true;
+        else sampler_name = argv[i];
+    }
+    g_stop_depth = levels;
+    bool boltz = strcmp(sampler_name, "boltzmann") == 0;
+    SamplerType* hook = boltz ? (SamplerType*) new GoldenHook<double>
+                              : (SamplerType*) new GoldenHook<NormalTheta<2> >;
+    /* same construction sequence as tree.cc:147-150 */
+    tree = new JobTree(cores, levels, hook, policy, correlation, dimension);
+    tree->set_reassign_ratio(reassign_ratio);
+    tree->set_require_comparison_theta(false);
+    tree->set_threshold(threshold);
+    double t0 = timestamp();
+    (void) t0;
+    if (boltz) {
+        MasterTester<BoltzmannSampler> mt(cores, 0, data_size, batch_size, BoltzmannSampler());
+        mt.run(*tree);
+    } else {
+        double* data = normal_dataset(data_size);
+        NormalSampler<2> sampler(data, data_size);
+        MasterTester<NormalSampler<2> > mt(cores, 0, data_size, batch_size, sampler);
+        mt.run(*tree);
+    }
+    return 0;
+}
+
+struct EvalHeader {
+    uint64_t n, nodes, theta_len;
+};
+
+/* IN : EvalHeader, double data[n][2], double theta[nodes][5]
+ * OUT: double (sum, sum_sq)[nodes]   -- reference visiting order (StrideIndex drawn in
+ *      prepare(), normalsampler.hh:115-119) with the replay stream at position 0. */
+int cmd_normal_eval(const char* in, const char* out) {
+    FILE* f = fopen(in, "rb");
+    if (!f) return 2;
+    EvalHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1) return 2;
+    std::vector<double> data(h.n * 2), theta(h.nodes * h.theta_len);
+    if (fread(data.data(), 8, data.size(), f) != data.size()) return 2;
+    if (fread(theta.data(), 8, theta.size(), f) != theta.size()) return 2;
+    fclose(f);
+    assert(h.theta_len == (uint64_t) NormalTheta<2>::size);
+    NormalSampler<2> s(data.data(), h.n);
+    std::vector<double> res(h.nodes * 2);
+    for (size_t b = 0; b != h.nodes; ++b) {
+        JobInfo job;
+        job.state = JobInfo::s_has_proposal;
+        job.random_position = 0;
+        job.theta = save_theta(NormalTheta<2>(&theta[b * h.theta_len]));
+        (void) s.load(job);
+        s.prepare();
+        double sum = 0, sq = 0;
+        s.evaluate_many(0, h.n, sum, sq);
+        res[2 * b] = sum;
+        res[2 * b + 1] = sq;
+    }
+    f = fopen(out, "wb");
+    fwrite(res.data(), 8, res.size(), f);
+    fclose(f);
+    return 0;
+}
+
+/* IN : EvalHeader (n = count, theta_len = 1), double theta[nodes]; OUT as above. */
+int cmd_boltz_eval(const char* in, const char* out) {
+    FILE* f = fopen(in, "rb");
+    if (!f) return 2;
+    EvalHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1) return 2;
+    std::vector<double> theta(h.nodes);
+    if (fread(theta.data(), 8, theta.size(), f) != theta.size()) return 2;
+    fclose(f);
+    BoltzmannSampler s;
+    std::vector<double> res(h.nodes * 2);
+    for (size_t b = 0; b != h.nodes; ++b) {
+        JobInfo job;
+        job.state = JobInfo::s_has_proposal;
+        job.random_position = 0;
+        job.theta = save_theta(theta[b]);
+        (void) s.load(job);
+        s.prepare();
+        double sum = 0, sq = 0;
+        s.evaluate_many(0, h.n, sum, sq);
+        res[2 * b] = sum;
+        res[2 * b + 1] = sq;
+    }
+    f = fopen(out, "wb");
+    fwrite(res.data(), 8, res.size(), f);
+    fclose(f);
+    return 0;
+}
+
+/* CPU baseline, kind "reference": B frontier nodes, each scored over all n points by the
+ * reference's own NormalSampler<2>::evaluate_many on its own thread -- the in-process
+ * analogue of `mpirun -np B+1 ./fetching` where every worker holds the whole dataset
+ * (normal.cc:43-48) and scores one node (worker.hh:148-155).  Prints one JSON line. */
+int cmd_normal_bench(size_t n, size_t nodes, size_t reps, size_t threads) {
+    double* data = normal_dataset(n);
+    if (threads == 0) threads = std::thread::hardware_concurrency();
+    if (threads > nodes) threads = nodes;
+    std::vector<double> sums(nodes, 0.0);
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t r = 0; r != reps; ++r) {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t != threads; ++t)
+            pool.emplace_back([&, t]() {
+                NormalSampler<2> s(data, n);
+                for (size_t b = t; b < nodes; b += threads) {
+                    double th[5] = {0.01 * (double) b, -0.02 * (double) b, 1, 0, 1};
+                    JobInfo job;
+                    job.state = JobInfo::s_has_proposal;
+                    job.random_position = 0;
+                    job.theta = save_theta(NormalTheta<2>(th));
+                    (void) s.load(job);
+                    s.prepare();
+                    double sum = 0, sq = 0;
+                    s.evaluate_many(0, n, sum, sq);
+                    sums[b] = sum;
+                }
+            });
+        for (auto& th : pool) th.join();
+    }
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"kind\": \"reference\", \"what\": \"NormalSampler<2>::evaluate_many\", \"n\": %zu, "
+           "\"nodes\": %zu, \"reps\": %zu, \"threads\": %zu, \"seconds\": %.6f, "
+           "\"evals_per_sec\": %.6f, \"item_evals_per_sec\": %.1f, \"check\": %.17g}\n",
+           n, nodes, reps, threads, dt, nodes * reps / dt, (double) n * nodes * reps / dt, sums[0]);
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: pf_ref unit | chain [normal|boltzmann] [-n C] [-d N] [-b B] [-l L] [-s P] "
+                        "[-D dim] [-r R] [-c C] [-t] | normal-eval IN OUT | boltz-eval IN OUT | "
+                        "normal-bench N NODES REPS [THREADS] | data N\n");
+        return 1;
+    }
+    std::string cmd = argv[1];
+    if (cmd == "unit") {
+        test_random_sequence();
+        test_proposals();
+        test_proposals2();
+        printf("reference unit tests: test_random_sequence test_proposals test_proposals2 OK\n");
+        return 0;
+    } else if (cmd == "chain")
+        return cmd_chain(argc - 2, argv + 2);
+    else if (cmd == "normal-eval" && argc == 4)
+        return cmd_normal_eval(argv[2], argv[3]);
+    else if (cmd == "boltz-eval" && argc == 4)
+        return cmd_boltz_eval(argv[2], argv[3]);
+    else if (cmd == "normal-bench" && argc >= 5)
+        return cmd_normal_bench(strtoull(argv[2], 0, 0), strtoull(argv[3], 0, 0),
+                                strtoull(argv[4], 0, 0), argc > 5 ? strtoull(argv[5], 0, 0) : 0);
+    else if (cmd == "data" && argc == 3) {
+        size_t n = strtoull(argv[2], 0, 0);
+        double* d = normal_dataset(n);
+        for (size_t i = 0; i != n * 2; ++i) printf("%.17g\n", d[i]);
+        return 0;
+    }
+    return 1;
+}
