@@ -1,0 +1,187 @@
+// pf_common.cuh -- device-side building blocks shared by the frontier kernels (sm_100a).
+//
+// * mbarrier + cp.async.bulk (TMA) wrappers: data tiles are staged into shared memory by the
+//   copy engine (SASS: UBLKCP for the 1-D form, UTMALDG for the tensor-map form) and signalled
+//   through transaction barriers, so no thread spends issue slots or registers on loads.
+// * fixed-order reductions: no floating-point atomics anywhere, so results are run-to-run
+//   bit-stable for a given launch geometry.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pf_engine.h"
+
+namespace pf {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make mbarrier.init visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// 2-D tiled TMA load: box at (c0 = innermost coordinate, c1 = row) of `map` -> shared.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// named barrier over `count` threads (the consumer warps only; the producer warp never joins)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+
+// sum over the lanes that differ from this one in bits [lo_bit .. 16]: butterfly, fixed order
+__device__ __forceinline__ double warp_sum_from(double v, int first_mask) {
+    for (int m = 16; m >= first_mask; m >>= 1) v += shfl_xor_f64(v, m);
+    return v;
+}
+
+__device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
+
+// ---------------------------------------------------------------------------------------------
+// Item assembly.  metric_sum_sq is a sum of squares of ITEM totals (worker.hh:151-152), so row
+// contributions must be summed per item before squaring.  A CTA scores a contiguous row range
+// [r0, r1) in tiles that never straddle an item.  One owner thread per node folds tile totals
+// into item totals; an item cut by the CTA boundary is exported as a `head` (its beginning is
+// in an earlier CTA) or `tail` (its end is in a later CTA) partial, and finalize_items() stitches
+// those in CTA order.  Everything is a fixed-order sum: bit-stable for a given geometry.
+// Per-CTA record layout: [S | Q | head | tail][kMaxNodesPerPass].
+// ---------------------------------------------------------------------------------------------
+struct ItemOwner {
+    double S, Q, run, head, tail;
+    bool from_start, open;
+    __device__ __forceinline__ void init(unsigned long long r0, unsigned long long item_rows) {
+        S = Q = run = head = tail = 0.0;
+        from_start = (item_rows <= 1) || (r0 % item_rows == 0);
+        open = false;
+    }
+    // `tot` = this node's total over tile [.., t1)
+    __device__ __forceinline__ void add_tile(double tot, unsigned long long t1, unsigned long long item_rows,
+                                             unsigned long long row_end) {
+        run += tot;
+        const bool closes = (t1 % item_rows == 0) || (t1 == row_end);
+        if (closes) {
+            if (from_start) {
+                S += run;
+                Q = fma(run, run, Q);
+            } else
+                head = run;
+            run = 0.0;
+            from_start = true;
+        }
+        open = !closes;
+    }
+    __device__ __forceinline__ void finish() {
+        if (open) {
+            if (from_start)
+                tail = run;
+            else
+                head = run;  // the whole CTA lies inside one item
+        }
+    }
+    __device__ __forceinline__ void store(double* rec, unsigned tid) const {
+        rec[0 * kMaxNodesPerPass + tid] = S;
+        rec[1 * kMaxNodesPerPass + tid] = Q;
+        rec[2 * kMaxNodesPerPass + tid] = head;
+        rec[3 * kMaxNodesPerPass + tid] = tail;
+    }
+};
+
+__device__ __forceinline__ void finalize_items(const double* part, unsigned grid, unsigned long long row_begin,
+                                               unsigned long long row_end, unsigned long long rows_per_cta,
+                                               unsigned long long item_rows, unsigned tid, double& S_out,
+                                               double& Q_out) {
+    double S = 0.0, Q = 0.0, carry = 0.0;
+    for (unsigned c = 0; c < grid; ++c) {
+        unsigned long long c0 = row_begin + (unsigned long long) c * rows_per_cta;
+        if (c0 >= row_end) break;
+        unsigned long long c1 = c0 + rows_per_cta;
+        if (c1 > row_end) c1 = row_end;
+        const double* pr = part + (size_t) c * 4 * kMaxNodesPerPass + tid;
+        if (item_rows <= 1) {
+            S += ld_cg_f64(pr);
+            Q += ld_cg_f64(pr + kMaxNodesPerPass);
+            continue;
+        }
+        const bool head_open = (c0 % item_rows) != 0;
+        if (head_open) {
+            carry += ld_cg_f64(pr + 2 * kMaxNodesPerPass);
+            unsigned long long ie = (c0 / item_rows + 1) * item_rows;
+            if (ie > row_end) ie = row_end;
+            if (ie <= c1) {  // the cut item ends inside this CTA
+                S += carry;
+                Q = fma(carry, carry, Q);
+                carry = 0.0;
+            }
+        }
+        S += ld_cg_f64(pr);
+        Q += ld_cg_f64(pr + kMaxNodesPerPass);
+        const unsigned long long ls = ((c1 - 1) / item_rows) * item_rows;
+        unsigned long long le = ls + item_rows;
+        if (le > row_end) le = row_end;
+        if (le > c1 && ls >= c0 && (ls > c0 || !head_open)) carry = ld_cg_f64(pr + 3 * kMaxNodesPerPass);
+    }
+    S_out = S;
+    Q_out = Q;
+}
+
+}  // namespace pf

@@ -1,0 +1,495 @@
+// pf_engine.cu -- the C ABI declared in include/pfetch.h: engine lifetime, data residency,
+// host- and device-pointer evaluation paths, NCCL all-reduce of the per-node partials.
+//
+// There is NO CPU fallback anywhere in this file: a missing sm_100 device is PF_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pf_engine.h"
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define PF_HAVE_NCCL_H 1
+#else
+#define PF_HAVE_NCCL_H 0
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+#endif
+
+namespace pf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define PF_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t err__ = (call);                                                          \
+        if (err__ != cudaSuccess) {                                                          \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return PF_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ NCCL (dlopen)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (decltype(api.GetUniqueId)) dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank)) dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy)) dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce)) dlsym(api.handle, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString)) dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce) return nullptr;
+    return &api;
+}
+
+static int allreduce_out(Engine& e, double* d_out, uint32_t B, cudaStream_t s) {
+    if (!e.nccl_comm || e.nranks <= 1) return PF_OK;
+    NcclApi* n = nccl_api();
+    if (!n) {
+        set_error("NCCL library not loadable");
+        return PF_ERR_NCCL;
+    }
+    // 2*B doubles: latency bound (<= 1 KB); NCCL picks its LL protocol over NVLink/NVSwitch
+    ncclResult_t r = n->AllReduce(d_out, d_out, (size_t) 2 * B, /*ncclDouble*/ 8, /*ncclSum*/ 0,
+                                  (ncclComm_t) e.nccl_comm, s);
+    if (r != 0) {
+        set_error("ncclAllReduce: %s", n->GetErrorString ? n->GetErrorString(r) : "error");
+        return PF_ERR_NCCL;
+    }
+    return PF_OK;
+}
+
+// ------------------------------------------------------------------------------------ helpers
+static bool is_matvec(const Engine& e) {
+    return e.desc.model == PF_MODEL_BLASSO || e.desc.model == PF_MODEL_BOLTZMANN_DENSE;
+}
+
+static int launch_model(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
+                        uint64_t n_items, cudaStream_t s) {
+    int r;
+    switch (e.desc.model) {
+        case PF_MODEL_NORMAL:
+        case PF_MODEL_MIXTURE: r = launch_pointwise(e, B, d_theta, d_out, first_item, n_items, s); break;
+        case PF_MODEL_BLASSO:
+        case PF_MODEL_BOLTZMANN_DENSE: r = launch_matvec(e, B, d_theta, d_out, first_item, n_items, s); break;
+        case PF_MODEL_BOLTZMANN_SCALAR: r = launch_boltzmann_scalar(e, B, d_theta, d_out, n_items, s); break;
+        default: set_error("unknown model"); return PF_ERR_INVALID;
+    }
+    if (r < 0) return PF_ERR_CUDA;
+    e.launches += (uint64_t) r;
+    return PF_OK;
+}
+
+static bool all_identity_cov(const Engine& e, const double* thetas, uint32_t B) {
+    const uint32_t D = e.dim;
+    for (uint32_t b = 0; b < B; ++b) {
+        const double* th = thetas + (size_t) b * e.theta_len;
+        for (uint32_t i = 0, x = 0; i < D; ++i)
+            for (uint32_t j = 0; j <= i; ++j, ++x)
+                if (th[D + x] != (j == i ? 1.0 : 0.0)) return false;  // normaltheta.hh:116-125
+    }
+    return true;
+}
+
+static void destroy(Engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->nccl_comm) {
+        NcclApi* n = nccl_api();
+        if (n && n->CommDestroy) n->CommDestroy((ncclComm_t) e->nccl_comm);
+    }
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_data);
+    cudaFree(e->d_resp);
+    cudaFree(e->d_theta);
+    cudaFree(e->d_out);
+    cudaFree(e->d_part);
+    cudaFree(e->d_betaT);
+    cudaFree(e->d_ticket);
+    if (e->h_theta) cudaFreeHost(e->h_theta);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int create(const pf_model_desc* d, Engine** out) {
+    if (!d || !out) {
+        set_error("null argument");
+        return PF_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || d->device < 0 || d->device >= ndev) {
+        set_error("no CUDA device %d (found %d); this engine has no CPU fallback", d->device, ndev);
+        return PF_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; the kernels are built for sm_100a only", d->device, prop.major, prop.minor);
+        return PF_ERR_NO_DEVICE;
+    }
+    PF_CUDA(cudaSetDevice(d->device));
+
+    Engine* e = new Engine();
+    e->desc = *d;
+    e->desc.data = nullptr;
+    e->desc.response = nullptr;
+    e->device = d->device;
+    e->sm_count = prop.multiProcessorCount;
+    e->f32 = d->dtype == PF_F32;
+    e->dim = d->dim;
+    e->K = d->components;
+    e->n_rows = d->n_rows;
+    e->temperature = d->param != 0.0 ? d->param : 1.0;
+
+    auto fail = [&](int code) {
+        destroy(e);
+        return code;
+    };
+    if (d->dtype != PF_F64 && d->dtype != PF_F32) {
+        set_error("unknown dtype %d", d->dtype);
+        return fail(PF_ERR_INVALID);
+    }
+
+    switch (d->model) {
+        case PF_MODEL_NORMAL:
+            if (!d->data || d->n_rows == 0 || d->dim == 0) { set_error("normal: data/n_rows/dim required"); return fail(PF_ERR_SHAPE); }
+            e->item_rows = 1;
+            e->n_items = d->n_items ? d->n_items : d->n_rows;
+            e->theta_len = d->dim + d->dim * (d->dim + 1) / 2;
+            break;
+        case PF_MODEL_MIXTURE:
+            if (!d->data || d->n_rows == 0 || d->dim == 0 || d->components == 0 || d->components > 32) {
+                set_error("mixture: data, n_rows, dim and 1 <= components <= 32 required");
+                return fail(PF_ERR_SHAPE);
+            }
+            e->item_rows = d->item_rows ? d->item_rows : (d->n_rows >= 100 ? d->n_rows / 100 : 1);  // pymixture.py:195
+            if (d->n_items)
+                e->n_items = d->n_items;
+            else {
+                e->n_items = (d->n_rows + 1) / e->item_rows;  // pymixture.py:64
+                // the reference cannot score a short last item (pymixture.py:88-91): whole items only
+                if (e->n_items * e->item_rows > d->n_rows) e->n_items = d->n_rows / e->item_rows;
+            }
+            e->theta_len = d->components * d->dim;
+            break;
+        case PF_MODEL_BLASSO:
+            if (!d->data || !d->response || d->n_rows == 0 || d->dim == 0) {
+                set_error("lasso: data, response, n_rows, dim required");
+                return fail(PF_ERR_SHAPE);
+            }
+            e->item_rows = d->item_rows ? d->item_rows : 18000;  // pyblasso.py:136-137
+            e->n_items = d->n_items ? d->n_items : d->n_rows / e->item_rows;  // pyblasso.py:69
+            e->theta_len = d->dim + 1;
+            break;
+        case PF_MODEL_BOLTZMANN_DENSE:
+            if (!d->data || d->dim == 0 || d->n_rows != d->dim) {
+                set_error("dense Boltzmann: W must be dim x dim (n_rows == dim)");
+                return fail(PF_ERR_SHAPE);
+            }
+            e->item_rows = d->n_rows;
+            e->n_items = 1;
+            e->theta_len = d->dim;
+            break;
+        case PF_MODEL_BOLTZMANN_SCALAR:
+            e->item_rows = 1;
+            e->n_items = d->n_items ? d->n_items : (d->n_rows ? d->n_rows : 1);
+            e->n_rows = e->n_items;
+            e->theta_len = 1;
+            break;
+        default:
+            set_error("unknown model %d", d->model);
+            return fail(PF_ERR_INVALID);
+    }
+    if (d->model != PF_MODEL_BOLTZMANN_SCALAR && d->model != PF_MODEL_BOLTZMANN_DENSE &&
+        (e->n_items == 0 || e->n_items * e->item_rows > e->n_rows)) {
+        set_error("n_items (%llu) x item_rows (%llu) inconsistent with n_rows (%llu)",
+                  (unsigned long long) e->n_items, (unsigned long long) e->item_rows, (unsigned long long) e->n_rows);
+        return fail(PF_ERR_SHAPE);
+    }
+    if ((d->model == PF_MODEL_NORMAL || d->model == PF_MODEL_MIXTURE) && !pointwise_supported(*e)) {
+        set_error("dimension %u not built for this model (1,2,3,4,8)", d->dim);
+        return fail(PF_ERR_UNSUPPORTED);
+    }
+    e->max_frontier = is_matvec(*e) || d->model == PF_MODEL_BOLTZMANN_SCALAR ? 64 : pointwise_max_frontier(*e);
+
+#define PF_CUDA_F(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            set_error("%s failed: %s", #call, cudaGetErrorString(err__));                    \
+            return fail(err__ == cudaErrorMemoryAllocation ? PF_ERR_NOMEM : PF_ERR_CUDA);    \
+        }                                                                                     \
+    } while (0)
+
+    PF_CUDA_F(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t esz = e->f32 ? 4 : 8;
+
+    // ---- data set -> device, once
+    if (d->model == PF_MODEL_NORMAL || d->model == PF_MODEL_MIXTURE) {
+        const size_t elems = (size_t) e->n_rows * e->dim;
+        const size_t bytes = ((elems * esz + 15) & ~size_t(15)) + 64;  // tail slack for the aligned copy window
+        PF_CUDA_F(cudaMalloc(&e->d_data, bytes));
+        PF_CUDA_F(cudaMemsetAsync(e->d_data, 0, bytes, e->stream));
+        if (!e->f32) {
+            PF_CUDA_F(cudaMemcpyAsync(e->d_data, d->data, elems * 8, cudaMemcpyHostToDevice, e->stream));
+            PF_CUDA_F(cudaStreamSynchronize(e->stream));
+        } else {
+            const size_t chunk = size_t(1) << 24;
+            std::vector<float> tmp(elems < chunk ? elems : chunk);
+            for (size_t o = 0; o < elems; o += chunk) {
+                const size_t n = elems - o < chunk ? elems - o : chunk;
+                for (size_t i = 0; i < n; ++i) tmp[i] = (float) d->data[o + i];
+                PF_CUDA_F(cudaMemcpyAsync((float*) e->d_data + o, tmp.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+                PF_CUDA_F(cudaStreamSynchronize(e->stream));
+            }
+        }
+    } else if (is_matvec(*e)) {
+        const uint32_t kch = (uint32_t) (128 / esz);
+        e->cols_pad = (e->dim + kch - 1) / kch * kch;  // row pitch in elements (multiple of one 128-byte chunk)
+        const size_t pitch = (size_t) e->cols_pad * esz;
+        const size_t bytes = pitch * e->n_rows + 1024;
+        PF_CUDA_F(cudaMalloc(&e->d_data, bytes));
+        PF_CUDA_F(cudaMemsetAsync(e->d_data, 0, bytes, e->stream));
+        if (!e->f32) {
+            PF_CUDA_F(cudaMemcpy2DAsync(e->d_data, pitch, d->data, (size_t) e->dim * 8, (size_t) e->dim * 8, e->n_rows,
+                                        cudaMemcpyHostToDevice, e->stream));
+            PF_CUDA_F(cudaStreamSynchronize(e->stream));
+        } else {
+            const size_t rows_chunk = ((size_t(1) << 24) / e->dim) ? ((size_t(1) << 24) / e->dim) : 1;
+            std::vector<float> tmp(rows_chunk * e->dim);
+            for (size_t r = 0; r < e->n_rows; r += rows_chunk) {
+                const size_t nr = e->n_rows - r < rows_chunk ? e->n_rows - r : rows_chunk;
+                for (size_t i = 0; i < nr * e->dim; ++i) tmp[i] = (float) d->data[r * e->dim + i];
+                PF_CUDA_F(cudaMemcpy2DAsync((char*) e->d_data + r * pitch, pitch, tmp.data(), (size_t) e->dim * 4,
+                                            (size_t) e->dim * 4, nr, cudaMemcpyHostToDevice, e->stream));
+                PF_CUDA_F(cudaStreamSynchronize(e->stream));
+            }
+        }
+        if (d->model == PF_MODEL_BLASSO) {
+            PF_CUDA_F(cudaMalloc(&e->d_resp, e->n_rows * 8));
+            PF_CUDA_F(cudaMemcpyAsync(e->d_resp, d->response, e->n_rows * 8, cudaMemcpyHostToDevice, e->stream));
+            PF_CUDA_F(cudaStreamSynchronize(e->stream));
+        }
+        PF_CUDA_F(cudaMalloc(&e->d_betaT, (size_t) e->cols_pad * kMaxNodesPerPass * esz));
+    }
+
+    // ---- per-call buffers
+    const size_t tbytes = (size_t) e->max_frontier * e->theta_len * 8;
+    PF_CUDA_F(cudaMalloc(&e->d_theta, tbytes));
+    PF_CUDA_F(cudaMalloc(&e->d_out, 2 * kMaxNodesPerPass * 8));
+    PF_CUDA_F(cudaMalloc(&e->d_part, (size_t) kMaxGrid * kPartSlots * kMaxNodesPerPass * 8));
+    PF_CUDA_F(cudaMalloc(&e->d_ticket, 64));
+    PF_CUDA_F(cudaMemsetAsync(e->d_ticket, 0, 64, e->stream));
+    PF_CUDA_F(cudaMallocHost(&e->h_theta, tbytes));
+    PF_CUDA_F(cudaMallocHost(&e->h_out, 2 * kMaxNodesPerPass * 8));
+    PF_CUDA_F(cudaStreamSynchronize(e->stream));
+#undef PF_CUDA_F
+    *out = e;
+    return PF_OK;
+}
+
+static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
+                     double* sum, double* sum_sq) {
+    PF_CUDA(cudaSetDevice(e.device));
+    for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
+        const uint32_t nb = B - b0 < e.max_frontier ? B - b0 : e.max_frontier;
+        const double* th = thetas + (size_t) b0 * e.theta_len;
+        if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !all_identity_cov(e, th, nb);
+        const size_t tbytes = (size_t) nb * e.theta_len * 8;
+        memcpy(e.h_theta, th, tbytes);
+        PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
+        int r = launch_model(e, nb, e.d_theta, e.d_out, first_item, n_items, e.stream);
+        if (r != PF_OK) return r;
+        r = allreduce_out(e, e.d_out, nb, e.stream);
+        if (r != PF_OK) return r;
+        PF_CUDA(cudaMemcpyAsync(e.h_out, e.d_out, (size_t) 2 * nb * 8, cudaMemcpyDeviceToHost, e.stream));
+        PF_CUDA(cudaStreamSynchronize(e.stream));
+        memcpy(sum + b0, e.h_out, (size_t) nb * 8);
+        memcpy(sum_sq + b0, e.h_out + nb, (size_t) nb * 8);
+    }
+    return PF_OK;
+}
+
+}  // namespace pf
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+using pf::Engine;
+
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+const char* pf_last_error(void) { return pf::g_err; }
+
+int pf_engine_create(const pf_model_desc* desc, pf_engine** out) {
+    Engine* e = nullptr;
+    int r = pf::create(desc, &e);
+    if (out) *out = reinterpret_cast<pf_engine*>(e);
+    return r;
+}
+
+void pf_engine_destroy(pf_engine* e) { pf::destroy(reinterpret_cast<Engine*>(e)); }
+
+uint64_t pf_engine_data_size(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->n_items : 0; }
+
+uint32_t pf_engine_theta_len(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->theta_len : 0; }
+
+uint32_t pf_engine_max_frontier(const pf_engine* e) {
+    return e ? reinterpret_cast<const Engine*>(e)->max_frontier : 0;
+}
+
+uint64_t pf_engine_launch_count(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->launches : 0; }
+
+int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
+    if (!pe) return PF_ERR_INVALID;
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    switch (option) {
+        case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
+    }
+    pf::set_error("unknown option %d", option);
+    return PF_ERR_INVALID;
+}
+
+int pf_eval_frontier(pf_engine* pe, uint32_t B, const double* thetas, double* sum, double* sum_sq) {
+    if (!pe || !thetas || !sum || !sum_sq || B == 0) {
+        pf::set_error("pf_eval_frontier: null argument or B == 0");
+        return PF_ERR_INVALID;
+    }
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    return pf::eval_host(e, B, thetas, 0, e.n_items, sum, sum_sq);
+}
+
+int pf_eval_frontier_range(pf_engine* pe, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
+                           const uint64_t* order, double* sum, double* sum_sq) {
+    if (!pe || !thetas || !sum || !sum_sq || B == 0) {
+        pf::set_error("pf_eval_frontier_range: null argument or B == 0");
+        return PF_ERR_INVALID;
+    }
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    if (first_item > e.n_items || n_items > e.n_items - first_item) {
+        pf::set_error("item range [%llu, +%llu) outside [0, %llu)", (unsigned long long) first_item,
+                      (unsigned long long) n_items, (unsigned long long) e.n_items);
+        return PF_ERR_SHAPE;
+    }
+    if (order) {
+        pf::set_error("StrideIndex-ordered partial ranges are not built yet");
+        return PF_ERR_UNSUPPORTED;
+    }
+    if (e.desc.model == PF_MODEL_BOLTZMANN_DENSE && n_items != 1) {
+        for (uint32_t b = 0; b < B; ++b) sum[b] = sum_sq[b] = 0.0;
+        return PF_OK;
+    }
+    return pf::eval_host(e, B, thetas, first_item, n_items, sum, sum_sq);
+}
+
+int pf_eval_frontier_device(pf_engine* pe, uint32_t B, const double* d_thetas, double* d_out, void* cuda_stream) {
+    if (!pe || !d_thetas || !d_out || B == 0) {
+        pf::set_error("pf_eval_frontier_device: null argument or B == 0");
+        return PF_ERR_INVALID;
+    }
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    if (B > e.max_frontier) {
+        pf::set_error("B = %u exceeds max_frontier = %u for the device-pointer path", B, e.max_frontier);
+        return PF_ERR_SHAPE;
+    }
+    if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e.stream;
+    if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !e.assume_identity;
+    int r = pf::launch_model(e, B, d_thetas, d_out, 0, e.n_items, s);
+    if (r != PF_OK) return r;
+    return pf::allreduce_out(e, d_out, B, s);
+}
+
+double pf_blasso_log_prior(const double* theta, uint32_t p, double tau) {
+    // pyblasso.py:123-133, same operation order
+    const double sigma = theta[0];
+    double l1 = 0.0;
+    for (uint32_t j = 0; j < p; ++j) l1 += fabs(theta[1 + j]);
+    const double log_prior_sigma = -2.0 * log(sigma);
+    const double log_laplace = p * log(tau / 2 / sigma) - (tau * l1) / sigma;
+    return log_prior_sigma + log_laplace;
+}
+
+int pf_nccl_unique_id(void* id128) {
+    if (!id128) return PF_ERR_INVALID;
+    pf::NcclApi* n = pf::nccl_api();
+    if (!n) {
+        pf::set_error("NCCL library not loadable");
+        return PF_ERR_NCCL;
+    }
+    ncclUniqueId id;
+    if (n->GetUniqueId(&id) != 0) {
+        pf::set_error("ncclGetUniqueId failed");
+        return PF_ERR_NCCL;
+    }
+    memcpy(id128, &id, 128);
+    return PF_OK;
+}
+
+int pf_engine_comm_init(pf_engine* pe, const void* id128, int rank, int nranks) {
+    if (!pe || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PF_ERR_INVALID;
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    e.rank = rank;
+    e.nranks = nranks;
+    if (nranks == 1) return PF_OK;
+    pf::NcclApi* n = pf::nccl_api();
+    if (!n) {
+        pf::set_error("NCCL library not loadable");
+        return PF_ERR_NCCL;
+    }
+    if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = n->CommInitRank(&comm, nranks, id, rank);
+    if (r != 0) {
+        pf::set_error("ncclCommInitRank: %s", n->GetErrorString ? n->GetErrorString(r) : "error");
+        return PF_ERR_NCCL;
+    }
+    e.nccl_comm = comm;
+    return PF_OK;
+}
+
+int pf_device_sm_count(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    return prop.multiProcessorCount;
+}
+
+}  // extern "C"

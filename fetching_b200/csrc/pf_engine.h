@@ -1,0 +1,93 @@
+// pf_engine.h -- internal (not part of the C ABI): engine state and kernel launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pfetch.h"
+
+namespace pf {
+
+constexpr int kMaxNodesPerPass = 64;  // frontier nodes scored by one kernel launch
+constexpr int kPartSlots = 4;        // per-CTA record: S, Q, head, tail
+constexpr int kMaxGrid = 148 * 4;    // upper bound on CTAs per launch (sizes the partial buffer)
+
+// Geometry of one launch of the pointwise (normal / mixture) kernels.
+struct PointwiseArgs {
+    const void* data;       // device, row-major [rows][dim] of T, 256-byte aligned, padded
+    const double* theta;    // device [B][theta_len]
+    double* part;           // device [grid][kPartSlots][64]
+    double* out;            // device [2][B]
+    unsigned int* ticket;   // device, zero between launches
+    unsigned long long row_begin, row_end;  // rows to score (whole items)
+    unsigned long long item_rows;           // rows per item (1: every row is an item)
+    unsigned int rows_per_cta;
+    unsigned int B, theta_len, K;
+};
+
+// Geometry of one launch of the streamed-matrix (lasso / dense Boltzmann) kernel.
+struct MatvecArgs {
+    CUtensorMap tmap;       // [rows][cols_pad] matrix, box = 16 doubles (or 32 floats) x ROWS, 128B swizzle
+    const double* theta;    // device [B][theta_len]
+    const void* betaT;      // device [cols_pad][Bpad] of T: coefficient panel, transposed by the prep kernel
+    const double* y;        // device [rows] (lasso) or nullptr
+    double* part;
+    double* out;
+    unsigned int* ticket;
+    unsigned long long row_begin, row_end;
+    unsigned long long item_rows;
+    unsigned int cols;      // p or D
+    unsigned int cols_pad;  // multiple of the k-chunk
+    unsigned int B, Bpad, theta_len;
+    unsigned int n_units;   // work units = row tiles x k splits
+    unsigned int k_splits;  // 1 for lasso; >1 only for the (linear) Boltzmann epilogue
+    unsigned int chunks_per_split;
+    unsigned int tile_rows;
+    unsigned long long rows_per_cta;  // lasso: contiguous rows per CTA (multiple of tile_rows)
+    double inv_temperature;
+};
+
+struct Engine {
+    pf_model_desc desc;
+    int device = 0;
+    int sm_count = 148;
+    bool f32 = false;
+    uint64_t n_rows = 0, n_items = 0, item_rows = 1;
+    uint32_t dim = 0, K = 0, theta_len = 0, max_frontier = 64;
+    uint32_t cols_pad = 0;
+    double temperature = 1.0;
+    bool normal_general = true;  // per call: some node has a non-identity covariance (or unknown)
+    bool assume_identity = false;  // PF_OPT_ASSUME_IDENTITY_COV
+
+    void* d_data = nullptr;      // data set (T), padded
+    double* d_resp = nullptr;    // lasso response (always double)
+    double* d_theta = nullptr;   // [max_frontier][theta_len]
+    double* d_out = nullptr;     // [2][max_frontier]
+    double* d_part = nullptr;    // [kMaxGrid][kPartSlots][64]
+    void* d_betaT = nullptr;     // matvec coefficient panel
+    unsigned int* d_ticket = nullptr;
+    double* h_theta = nullptr;   // pinned staging
+    double* h_out = nullptr;     // pinned staging
+    cudaStream_t stream = nullptr;
+    CUtensorMap tmaps[8];        // tensor maps by box height (cached)
+    unsigned tmap_rows[8] = {};
+    int n_tmaps = 0;
+
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    uint64_t launches = 0;
+};
+
+// launchers (defined in the .cu files); return the number of kernels launched or <0 on error
+int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
+                     uint64_t n_items, cudaStream_t s);
+int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
+                  uint64_t n_items, cudaStream_t s);
+int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,
+                            cudaStream_t s);
+uint32_t pointwise_max_frontier(const Engine& e);
+bool pointwise_supported(const Engine& e);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace pf

@@ -1,0 +1,474 @@
+// pf_matvec.cu -- frontier kernels for the models whose row term needs a dot product of the
+// data row with a per-node vector:
+//
+//   Bayesian lasso   pyblasso.py:135-141   lp_item = sum_rows [ log(1/sigma/sqrt(2pi)) - (beta.x_r - y_r)^2 / 2 / sigma^2 ]
+//   dense Boltzmann  (new workload)        log p   = -x'Wx / T  = -(1/T) sum_i x_i (W_i . x)
+//
+// Both stream a row-major matrix (X: n x p, W: D x D) exactly ONCE per launch and multiply it
+// by the B node vectors at the same time -- a tall-skinny GEMM fused with its row-wise epilogue
+// and the reduction over rows, so the n x B product never exists in memory.
+//
+// DESIGN (B200).  A producer warp walks (row tile x 128-byte column chunk) boxes of the matrix
+// with 2-D TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage shared-memory ring, together
+// with the matching [chunk][B] slice of the coefficient panel (1-D bulk copy; the panel is the
+// thetas transposed once per call by a tiny prep kernel and stays L2 resident).  Eight consumer
+// warps are arranged ROW-WARPS x NODE-GROUPS; a lane owns RPL rows x 8 nodes of accumulators.
+// Row operands are read with conflict-free LDS.128 thanks to the swizzle, coefficient operands
+// are warp-wide broadcasts, and every operand fetched from shared memory feeds 8 (row) or
+// RPL (coefficient) FP64 FMAs.  The epilogue (residual, square, scale / multiply by x_i) runs
+// in registers; item totals are assembled exactly like in pf_pointwise.cu.
+//
+// Arithmetic is FP64 FMA on the CUDA cores (the reference is IEEE double; sm_100a has no FP64
+// tcgen05 kind).  PF_F32 stores X/W and the panel as float and accumulates dots in float.
+#include <math.h>
+#include <stdio.h>
+
+#include "pf_common.cuh"
+#include "pf_engine.h"
+
+namespace pf {
+
+constexpr int MV_CONSUMER_WARPS = 8;
+constexpr int MV_CONSUMERS = MV_CONSUMER_WARPS * 32;
+constexpr int MV_THREADS = MV_CONSUMERS + 32;
+constexpr int MV_STAGES = 4;
+constexpr int MV_CHUNK_BYTES = 128;  // bytes of one matrix row per stage == the swizzle span
+constexpr int MV_MAX_TILE_ROWS = 256;
+constexpr int MV_NODES_PER_LANE = 8;
+constexpr int MV_XSTAGE_BYTES = MV_MAX_TILE_ROWS * MV_CHUNK_BYTES;                  // 32 KB
+constexpr int MV_BSTAGE_BYTES = MV_CHUNK_BYTES * kMaxNodesPerPass;                  // [chunk k][64 nodes] = 8 KB
+constexpr int MV_RED_DOUBLES = 2 * MV_CONSUMER_WARPS * kMaxNodesPerPass;
+
+constexpr size_t kMvSmem = 1024 /* alignment slack */ + (size_t) MV_STAGES * (MV_XSTAGE_BYTES + MV_BSTAGE_BYTES) +
+                           MV_RED_DOUBLES * sizeof(double) + 2 * MV_STAGES * sizeof(uint64_t) + 16;
+
+// transpose thetas into the coefficient panel: panel[k][b] = theta[b][off + k], zero padded
+template <typename T>
+__global__ void mv_prep_panel(const double* theta, T* panel, unsigned B, unsigned Bpad, unsigned theta_len,
+                              unsigned off, unsigned cols, unsigned cols_pad) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cols_pad * Bpad) return;
+    const unsigned k = idx / Bpad, b = idx % Bpad;
+    double v = 0.0;
+    if (k < cols && b < B) v = theta[(size_t) b * theta_len + off + k];
+    panel[idx] = (T) v;
+}
+
+// Work units.  Lasso: the CTA's contiguous row range cut into tiles that never straddle an item,
+// each over ALL column chunks (the epilogue is non-linear in the dot product).  Boltzmann: units
+// are (row tile, column split) pairs dealt round-robin to CTAs (the epilogue is linear).
+template <bool BOLTZ>
+struct UnitIter {
+    // lasso
+    unsigned long long cur, end_all, item_rows, row_end;
+    // boltzmann
+    unsigned u, n_units, stride, k_splits, chunks_per_split, n_chunks;
+    unsigned tile_rows;
+    unsigned long long row_begin;
+    __device__ __forceinline__ bool next(unsigned long long& t0, unsigned long long& t1, unsigned& c0, unsigned& c1) {
+        if constexpr (BOLTZ) {
+            if (u >= n_units) return false;
+            const unsigned tile = u / k_splits, split = u % k_splits;
+            t0 = row_begin + (unsigned long long) tile * tile_rows;
+            t1 = t0 + tile_rows;
+            if (t1 > row_end) t1 = row_end;
+            c0 = split * chunks_per_split;
+            c1 = c0 + chunks_per_split;
+            if (c1 > n_chunks) c1 = n_chunks;
+            u += stride;
+            return true;
+        } else {
+            if (cur >= end_all) return false;
+            t0 = cur;
+            unsigned long long e = cur + tile_rows;
+            if (e > end_all) e = end_all;
+            unsigned long long ie = (cur / item_rows + 1) * item_rows;
+            if (ie > row_end) ie = row_end;
+            if (e > ie) e = ie;
+            t1 = e;
+            cur = e;
+            c0 = 0;
+            c1 = n_chunks;
+            return true;
+        }
+    }
+};
+
+template <typename T, int RPL, bool BOLTZ>
+__global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid_constant__ MatvecArgs a) {
+    using CT = typename std::conditional<sizeof(T) == 4, float, double>::type;
+    constexpr int KPV = 16 / (int) sizeof(T);             // k values per 16-byte vector
+    constexpr int KCH = MV_CHUNK_BYTES / (int) sizeof(T);  // k values per chunk
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* xstage = smem;
+    unsigned char* bstage = smem + MV_STAGES * MV_XSTAGE_BYTES;
+    double* red = reinterpret_cast<double*>(bstage + MV_STAGES * MV_BSTAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + MV_RED_DOUBLES);
+    uint64_t* empty = full + MV_STAGES;
+    int* flag = reinterpret_cast<int*>(empty + MV_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned B = a.B, Bpad = a.Bpad;
+    const unsigned NG = Bpad / MV_NODES_PER_LANE;  // node groups: 1, 2, 4 or 8
+    const unsigned tile_rows = a.tile_rows;        // = (8 / NG) * 32 * RPL
+    const unsigned n_chunks = a.cols_pad / KCH;
+    const unsigned xbytes = tile_rows * MV_CHUNK_BYTES;
+    const unsigned bbytes = KCH * Bpad * (unsigned) sizeof(T);
+
+    unsigned long long r0 = a.row_begin, r1 = a.row_end;
+    if constexpr (!BOLTZ) {
+        const unsigned long long per = a.rows_per_cta;
+        r0 = a.row_begin + (unsigned long long) blockIdx.x * per;
+        if (r0 > a.row_end) r0 = a.row_end;
+        r1 = r0 + per;
+        if (r1 > a.row_end) r1 = a.row_end;
+    }
+    UnitIter<BOLTZ> proto{r0, r1, a.item_rows, a.row_end, blockIdx.x, a.n_units, gridDim.x, a.k_splits,
+                          a.chunks_per_split, n_chunks, tile_rows, a.row_begin};
+
+    if (tid == 0) {
+        for (int s = 0; s < MV_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], MV_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == MV_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            prefetch_tensormap(&a.tmap);
+            UnitIter<BOLTZ> it = proto;
+            unsigned long long t0, t1;
+            unsigned c0, c1, q = 0;
+            while (it.next(t0, t1, c0, c1)) {
+                for (unsigned c = c0; c < c1; ++c, ++q) {
+                    const unsigned s = q % MV_STAGES;
+                    if (q >= MV_STAGES) mbar_wait(&empty[s], ((q / MV_STAGES) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[s], xbytes + bbytes);
+                    tma_load_2d(xstage + s * MV_XSTAGE_BYTES, &a.tmap, (int) (c * KCH), (int) t0, &full[s]);
+                    bulk_g2s(bstage + s * MV_BSTAGE_BYTES,
+                             static_cast<const unsigned char*>(a.betaT) + (size_t) c * bbytes, bbytes, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const unsigned g = warp % NG, rw = warp / NG;  // node group, row warp
+    const unsigned row_in_tile = rw * (32 * RPL) + lane;  // + 32*i
+    const unsigned sw = lane & 7;                          // swizzle phase of all my rows
+
+    // per-node constants of the epilogue
+    double cst[MV_NODES_PER_LANE], hinv[MV_NODES_PER_LANE];
+#pragma unroll
+    for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+        unsigned node = g * MV_NODES_PER_LANE + n;
+        if (node >= B) node = B - 1;
+        if constexpr (BOLTZ) {
+            cst[n] = 0.0;
+            hinv[n] = 0.0;
+        } else {
+            const double sigma = a.theta[(size_t) node * a.theta_len];
+            cst[n] = log(1 / sigma / sqrt(2 * 3.14159265358979323846));  // pyblasso.py:140
+            hinv[n] = 1.0 / (2.0 * sigma * sigma);
+        }
+    }
+
+    ItemOwner own;
+    own.init(r0, BOLTZ ? 1ull : a.item_rows);
+
+    UnitIter<BOLTZ> it = proto;
+    unsigned long long t0, t1;
+    unsigned c0, c1, q = 0, unit = 0;
+    while (it.next(t0, t1, c0, c1)) {
+        CT acc[RPL][MV_NODES_PER_LANE];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int n = 0; n < MV_NODES_PER_LANE; ++n) acc[i][n] = 0;
+
+        for (unsigned c = c0; c < c1; ++c, ++q) {
+            const unsigned s = q % MV_STAGES;
+            mbar_wait(&full[s], (q / MV_STAGES) & 1);
+            const unsigned char* xs = xstage + s * MV_XSTAGE_BYTES + (size_t) row_in_tile * MV_CHUNK_BYTES;
+            const T* bs = reinterpret_cast<const T*>(bstage + s * MV_BSTAGE_BYTES) + g * MV_NODES_PER_LANE;
+#pragma unroll
+            for (int v = 0; v < MV_CHUNK_BYTES / 16; ++v) {
+                T xv[RPL][KPV];
+#pragma unroll
+                for (int i = 0; i < RPL; ++i)
+                    *reinterpret_cast<int4*>(xv[i]) =
+                        *reinterpret_cast<const int4*>(xs + (size_t) i * 32 * MV_CHUNK_BYTES + ((v ^ sw) << 4));
+#pragma unroll
+                for (int kk = 0; kk < KPV; ++kk) {
+                    T bv[MV_NODES_PER_LANE];
+                    const T* bp = bs + (size_t) (v * KPV + kk) * Bpad;
+#pragma unroll
+                    for (int w = 0; w < MV_NODES_PER_LANE * (int) sizeof(T) / 16; ++w)
+                        reinterpret_cast<int4*>(bv)[w] = reinterpret_cast<const int4*>(bp)[w];
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                        for (int n = 0; n < MV_NODES_PER_LANE; ++n)
+                            acc[i][n] = fma((CT) xv[i][kk], (CT) bv[n], acc[i][n]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        // ---- epilogue for this unit, in registers
+        double part[MV_NODES_PER_LANE];
+#pragma unroll
+        for (int n = 0; n < MV_NODES_PER_LANE; ++n) part[n] = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const unsigned long long r = t0 + row_in_tile + 32 * i;
+            if (r < t1) {
+                if constexpr (BOLTZ) {
+#pragma unroll
+                    for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+                        unsigned node = g * MV_NODES_PER_LANE + n;
+                        if (node >= B) node = B - 1;
+                        const double xi = __ldg(&a.theta[(size_t) node * a.theta_len + r]);
+                        part[n] = fma(xi, (double) acc[i][n], part[n]);
+                    }
+                } else {
+                    const double yv = __ldg(&a.y[r]);
+#pragma unroll
+                    for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+                        const double res = (double) acc[i][n] - yv;
+                        part[n] += cst[n] - res * res * hinv[n];
+                    }
+                }
+            }
+        }
+        double* rbuf = red + (unit & 1) * (MV_CONSUMER_WARPS * kMaxNodesPerPass);
+#pragma unroll
+        for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+            double v = part[n];
+            for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
+            if (lane == 0) rbuf[rw * kMaxNodesPerPass + g * MV_NODES_PER_LANE + n] = v;
+        }
+        named_bar_sync(1, MV_CONSUMERS);
+        if ((unsigned) tid < B) {
+            double tot = 0.0;
+            const unsigned RW = MV_CONSUMER_WARPS / NG;
+            for (unsigned w = 0; w < RW; ++w) tot += rbuf[w * kMaxNodesPerPass + tid];
+            if constexpr (BOLTZ)
+                own.S += tot;
+            else
+                own.add_tile(tot, t1, a.item_rows, a.row_end);
+        }
+        ++unit;
+    }
+
+    double* rec = a.part + (size_t) blockIdx.x * kPartSlots * kMaxNodesPerPass;
+    if ((unsigned) tid < B) {
+        if constexpr (!BOLTZ) own.finish();
+        own.store(rec, tid);
+        __threadfence();
+    }
+    named_bar_sync(1, MV_CONSUMERS);
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(a.ticket, 1u);
+        flag[0] = (prev == gridDim.x - 1);
+    }
+    named_bar_sync(1, MV_CONSUMERS);
+    if (!flag[0]) return;
+
+    __threadfence();
+    if ((unsigned) tid < B) {
+        if constexpr (BOLTZ) {
+            double E = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c)
+                E += ld_cg_f64(a.part + (size_t) c * kPartSlots * kMaxNodesPerPass + tid);
+            const double lp = -E * a.inv_temperature;  // one item: the whole energy
+            a.out[tid] = lp;
+            a.out[B + tid] = lp * lp;
+        } else {
+            double S, Q;
+            finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows, tid, S, Q);
+            a.out[tid] = S;
+            a.out[B + tid] = Q;
+        }
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
+    for (int i = 0; i < e.n_tmaps; ++i)
+        if (e.tmap_rows[i] == tile_rows) {
+            *out = e.tmaps[i];
+            return 0;
+        }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return -1;
+    }
+    const size_t esz = e.f32 ? 4 : 8;
+    const cuuint64_t dims[2] = {(cuuint64_t) e.dim, (cuuint64_t) e.n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t) e.cols_pad * esz};
+    const cuuint32_t box[2] = {(cuuint32_t) (MV_CHUNK_BYTES / esz), (cuuint32_t) tile_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, e.f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, e.d_data, dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int) r);
+        return -1;
+    }
+    if (e.n_tmaps < 8) {
+        e.tmaps[e.n_tmaps] = *out;
+        e.tmap_rows[e.n_tmaps++] = tile_rows;
+    }
+    return 0;
+}
+
+template <typename T, int RPL, bool BOLTZ>
+int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
+    auto kern = mv_frontier_kernel<T, RPL, BOLTZ>;
+    static bool configured_dev[64] = {};
+    if (!configured_dev[e.device & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMvSmem);
+        if (err != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(matvec): %s", cudaGetErrorString(err));
+            return -1;
+        }
+        configured_dev[e.device & 63] = true;
+    }
+    const unsigned long long rows = a.row_end - a.row_begin;
+    const unsigned KCH = MV_CHUNK_BYTES / sizeof(T);
+    const unsigned n_chunks = a.cols_pad / KCH;
+    unsigned grid;
+    if (BOLTZ) {
+        // enough (row tile, column split) units to occupy every SM
+        const unsigned long long tiles = (rows + a.tile_rows - 1) / a.tile_rows;
+        unsigned splits = 1;
+        while ((unsigned long long) tiles * splits < (unsigned long long) e.sm_count && splits < n_chunks) splits *= 2;
+        if (splits > n_chunks) splits = n_chunks;
+        a.chunks_per_split = (n_chunks + splits - 1) / splits;
+        a.k_splits = (n_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+        a.n_units = (unsigned) tiles * a.k_splits;
+        a.rows_per_cta = rows;
+        grid = a.n_units < (unsigned) e.sm_count ? a.n_units : (unsigned) e.sm_count;
+    } else {
+        // Contiguous rows per CTA, cut into equal tiles no taller than the lane layout allows, so
+        // every CTA streams the same number of full boxes and no box reads rows it will not use
+        // (HBM traffic == algorithmic bytes, except at item boundaries).
+        const unsigned max_tr = a.tile_rows;
+        unsigned long long g = (rows + 63) / 64;
+        if (g > (unsigned long long) e.sm_count) g = e.sm_count;
+        if (g < 1) g = 1;
+        unsigned long long per = (rows + g - 1) / g;
+        const unsigned long long tpc = (per + max_tr - 1) / max_tr;
+        unsigned long long tr = (per + tpc - 1) / tpc;
+        tr = (tr + 7) & ~7ull;
+        if (tr > max_tr) tr = max_tr;
+        per = tpc * tr;
+        a.tile_rows = (unsigned) tr;
+        a.rows_per_cta = per;
+        a.k_splits = 1;
+        a.chunks_per_split = n_chunks;
+        a.n_units = 0;
+        grid = (unsigned) ((rows + per - 1) / per);
+    }
+    if (make_tmap(e, a.tile_rows, &a.tmap) != 0) return -1;
+    if (grid < 1) grid = 1;
+    kern<<<grid, MV_THREADS, kMvSmem, s>>>(a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("matvec kernel launch: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 1;
+}
+
+template <typename T, bool BOLTZ>
+int dispatch_rpl(Engine& e, MatvecArgs& a, unsigned rpl, cudaStream_t s) {
+    switch (rpl) {
+        case 1: return launch_mv<T, 1, BOLTZ>(e, a, s);
+        case 2: return launch_mv<T, 2, BOLTZ>(e, a, s);
+        default: return launch_mv<T, 4, BOLTZ>(e, a, s);
+    }
+}
+
+}  // namespace
+
+int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
+                  uint64_t n_items, cudaStream_t s) {
+    const bool boltz = e.desc.model == PF_MODEL_BOLTZMANN_DENSE;
+    MatvecArgs a{};
+    unsigned NG = 1;
+    while (NG * MV_NODES_PER_LANE < B) NG *= 2;  // 1, 2, 4, 8
+    const unsigned rpl = NG == 1 ? 1 : (NG == 2 ? 2 : 4);
+    a.tile_rows = (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // 256, 256, 256, 128
+    a.B = B;
+    a.Bpad = NG * MV_NODES_PER_LANE;
+    a.theta = d_theta;
+    a.theta_len = e.theta_len;
+    a.betaT = e.d_betaT;
+    a.y = e.d_resp;
+    a.part = e.d_part;
+    a.out = d_out;
+    a.ticket = e.d_ticket;
+    a.cols = e.dim;
+    a.cols_pad = e.cols_pad;
+    a.item_rows = boltz ? e.n_rows : e.item_rows;
+    a.row_begin = boltz ? 0 : first_item * e.item_rows;
+    a.row_end = boltz ? e.n_rows : (first_item + n_items) * e.item_rows;
+    if (a.row_end > e.n_rows) a.row_end = e.n_rows;
+    a.inv_temperature = 1.0 / e.temperature;
+    if (a.row_end <= a.row_begin) {
+        cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
+        return 0;
+    }
+    const unsigned off = boltz ? 0 : 1;
+    const unsigned total = e.cols_pad * a.Bpad;
+    if (e.f32)
+        mv_prep_panel<float><<<(total + 255) / 256, 256, 0, s>>>(d_theta, static_cast<float*>(e.d_betaT), B, a.Bpad,
+                                                                 e.theta_len, off, e.dim, e.cols_pad);
+    else
+        mv_prep_panel<double><<<(total + 255) / 256, 256, 0, s>>>(d_theta, static_cast<double*>(e.d_betaT), B, a.Bpad,
+                                                                  e.theta_len, off, e.dim, e.cols_pad);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("mv_prep_panel launch: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    int r;
+    if (boltz)
+        r = e.f32 ? dispatch_rpl<float, true>(e, a, rpl, s) : dispatch_rpl<double, true>(e, a, rpl, s);
+    else
+        r = e.f32 ? dispatch_rpl<float, false>(e, a, rpl, s) : dispatch_rpl<double, false>(e, a, rpl, s);
+    return r < 0 ? r : r + 1;
+}
+
+}  // namespace pf

@@ -1,0 +1,557 @@
+// pf_pointwise.cu -- frontier kernels for the models whose item log-probability is a function
+// of one data row and the node's theta:
+//
+//   normal target   normalsampler.hh:128-154   lp_i = -1/2 (mu-x_i)' Winv (mu-x_i) + scale
+//   mixture         pymixture.py:86-92         lp_item = sum_rows log sum_k exp(-|theta_k - x_r|^2 / 2)
+//   scalar Boltzmann boltzmannsampler.hh:71-82 closed form, no data
+//
+// and per node the two numbers a reference worker accumulates (worker.hh:148-155):
+//   metric_sum = sum_items lp_item,   metric_sum_sq = sum_items lp_item^2.
+//
+// DESIGN (B200).  The data set is read from HBM exactly once per launch, whatever the
+// frontier size B.  Each CTA owns a contiguous row range; a producer warp streams it through a
+// 4-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier tx counts), and
+// eight consumer warps score every staged row against every node.  Lanes are split
+// NODES x POINT-LANES: lane l scores node (l mod NB) on the rows of point-lane (l / NB), so theta
+// lives in registers, row reads are shared-memory broadcasts, and per-node accumulators never
+// leave the lane.  For B > 32 each lane carries two nodes.  Reductions are fixed-order (warp
+// shuffle -> per-warp slots -> per-CTA record -> last-CTA finalize), so results are bit-stable
+// run to run; there are no floating-point atomics.
+//
+// ITEMS.  For the mixture an item is a batch of rows and metric_sum_sq needs the item totals
+// before squaring.  Tiles never straddle an item, a per-tile block reduction gives the tile
+// total, and one owner thread per node assembles item totals; items cut by a CTA boundary are
+// handed to the finalize step as head/tail partials and stitched there in CTA order.
+#include <math.h>
+#include <stdio.h>
+
+#include "pf_common.cuh"
+#include "pf_engine.h"
+
+namespace pf {
+
+constexpr int PW_CONSUMER_WARPS = 8;
+constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
+constexpr int PW_THREADS = PW_CONSUMERS + 32;  // + one producer warp
+constexpr int PW_STAGES = 4;
+constexpr int PW_TILE_BYTES = 16384;
+constexpr int PW_STAGE_BYTES = PW_TILE_BYTES + 32;  // room for the 16-byte aligned copy window
+constexpr int PW_RED_DOUBLES = 2 * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+constexpr double kLog2Pi = 1.837877066409345483560659472810;  // normalsampler.hh:24-26
+
+template <typename T> struct ComputeOf { using type = double; };
+template <> struct ComputeOf<float> { using type = float; };
+
+__device__ __forceinline__ double pf_exp(double x) { return exp(x); }
+__device__ __forceinline__ float pf_exp(float x) { return expf(x); }
+__device__ __forceinline__ double pf_log(double x) { return log(x); }
+__device__ __forceinline__ float pf_log(float x) { return logf(x); }
+
+// ---------------------------------------------------------------------------------------------
+// row loader: DIM values of T from shared memory (alignment = gcd(16, DIM*sizeof(T)))
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DIM, typename CT>
+__device__ __forceinline__ void load_row(const unsigned char* p, CT (&x)[DIM]) {
+    constexpr int RB = DIM * (int) sizeof(T);
+    T tmp[DIM];
+    if constexpr (RB % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < RB / 16; ++i) reinterpret_cast<int4*>(tmp)[i] = reinterpret_cast<const int4*>(p)[i];
+    } else if constexpr (RB % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < RB / 8; ++i) reinterpret_cast<int2*>(tmp)[i] = reinterpret_cast<const int2*>(p)[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < RB / 4; ++i) reinterpret_cast<int*>(tmp)[i] = reinterpret_cast<const int*>(p)[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) x[i] = (CT) tmp[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model policies
+// ---------------------------------------------------------------------------------------------
+// Gaussian target.  theta = D means + packed lower-triangular covariance (normaltheta.hh:81-87).
+// prepare() of the reference (normalsampler.hh:87-113): identity covariance -> scale = -D log(2pi)/2;
+// otherwise LU-invert the covariance, scale = -(D log 2pi + log det)/2, and evaluate() uses the
+// UPPER triangle of the inverse as a symmetric matrix (dsymv CblasUpper, :145).
+template <int D, typename T, bool GENERAL>
+struct NormalModel {
+    static constexpr int DIM = D;
+    static constexpr bool ITEM1 = true;
+    using CT = typename ComputeOf<T>::type;
+    struct Node {
+        CT mu[D];
+        CT w[GENERAL ? D * (D + 1) / 2 : 1];  // upper triangle of Winv, row-major, off-diagonals doubled
+        CT scale;
+    };
+    static __device__ void load(Node& nd, const double* th, unsigned) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) nd.mu[i] = (CT) th[i];
+        if constexpr (!GENERAL) {
+            nd.w[0] = 0;
+            nd.scale = (CT) (-D * kLog2Pi / 2);
+        } else {
+            double A[D][D], inv[D][D];
+            int perm[D];
+            for (int i = 0, idx = 0; i < D; ++i)
+                for (int j = 0; j <= i; ++j, ++idx) A[i][j] = A[j][i] = th[D + idx];
+            int signum = 1;
+            for (int i = 0; i < D; ++i) perm[i] = i;
+            for (int j = 0; j + 1 < D; ++j) {  // partial pivoting, as gsl_linalg_LU_decomp
+                double mx = fabs(A[j][j]);
+                int piv = j;
+                for (int i = j + 1; i < D; ++i)
+                    if (fabs(A[i][j]) > mx) { mx = fabs(A[i][j]); piv = i; }
+                if (piv != j) {
+                    for (int k = 0; k < D; ++k) { double t = A[j][k]; A[j][k] = A[piv][k]; A[piv][k] = t; }
+                    int t = perm[j]; perm[j] = perm[piv]; perm[piv] = t;
+                    signum = -signum;
+                }
+                double ajj = A[j][j];
+                if (ajj != 0.0)
+                    for (int i = j + 1; i < D; ++i) {
+                        double aij = A[i][j] / ajj;
+                        A[i][j] = aij;
+                        for (int k = j + 1; k < D; ++k) A[i][k] -= aij * A[j][k];
+                    }
+            }
+            for (int c = 0; c < D; ++c) {
+                double x[D];
+                for (int i = 0; i < D; ++i) x[i] = (perm[i] == c) ? 1.0 : 0.0;
+                for (int i = 0; i < D; ++i)
+                    for (int k = 0; k < i; ++k) x[i] -= A[i][k] * x[k];
+                for (int i = D - 1; i >= 0; --i) {
+                    for (int k = i + 1; k < D; ++k) x[i] -= A[i][k] * x[k];
+                    x[i] /= A[i][i];
+                }
+                for (int i = 0; i < D; ++i) inv[i][c] = x[i];
+            }
+            double det = (double) signum;
+            for (int i = 0; i < D; ++i) det *= A[i][i];
+            for (int i = 0, idx = 0; i < D; ++i)
+                for (int j = i; j < D; ++j, ++idx) nd.w[idx] = (CT) (i == j ? inv[i][j] : 2.0 * inv[i][j]);
+            nd.scale = (CT) (-(D * kLog2Pi + log(det)) / 2);
+        }
+    }
+    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+        CT t[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) t[i] = nd.mu[i] - x[i];
+        CT dot = 0;
+        if constexpr (!GENERAL) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) dot = fma(t[i], t[i], dot);
+        } else {
+            int idx = 0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = i; j < D; ++j, ++idx) dot = fma(nd.w[idx] * t[i], t[j], dot);
+        }
+        return fma((CT) -0.5, dot, nd.scale);
+    }
+};
+
+// Gaussian mixture with unit-variance spherical components, unnormalised (pymixture.py:86-92).
+// The reference multiplies d one-dimensional exps per component; exp of the summed exponent is
+// the same number to rounding (<= d ulp) and costs one exp instead of d.
+template <int K, int D, typename T>
+struct MixtureModel {
+    static constexpr int DIM = D;
+    static constexpr bool ITEM1 = false;
+    using CT = typename ComputeOf<T>::type;
+    struct Node {
+        CT th[K * D];
+    };
+    static __device__ void load(Node& nd, const double* th, unsigned) {
+#pragma unroll
+        for (int i = 0; i < K * D; ++i) nd.th[i] = (CT) th[i];
+    }
+    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+        CT lp = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            CT e = 0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                CT t = nd.th[k * D + j] - x[j];
+                e = fma(t, t, e);
+            }
+            lp += pf_exp((CT) -0.5 * e);
+        }
+        return pf_log(lp);
+    }
+};
+
+// Any K (<= 32): theta stays in global/L1 (read-only, broadcast across point-lanes).  Fallback
+// for shapes without a register-resident instantiation.
+template <int D, typename T>
+struct MixtureModelRT {
+    static constexpr int DIM = D;
+    static constexpr bool ITEM1 = false;
+    using CT = typename ComputeOf<T>::type;
+    struct Node {
+        const double* th;
+        unsigned K;
+    };
+    static __device__ void load(Node& nd, const double* th, unsigned K) {
+        nd.th = th;
+        nd.K = K;
+    }
+    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+        CT lp = 0;
+        for (unsigned k = 0; k < nd.K; ++k) {
+            CT e = 0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                CT t = (CT) __ldg(&nd.th[k * D + j]) - x[j];
+                e = fma(t, t, e);
+            }
+            lp += pf_exp((CT) -0.5 * e);
+        }
+        return pf_log(lp);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// tile walk shared by producer and consumers: contiguous rows, cut at item boundaries
+// ---------------------------------------------------------------------------------------------
+struct TileIter {
+    unsigned long long cur, end_all, item_rows, row_end;
+    unsigned tile_rows;
+    __device__ __forceinline__ bool next(unsigned long long& t0, unsigned long long& t1) {
+        if (cur >= end_all) return false;
+        t0 = cur;
+        unsigned long long e = cur + tile_rows;
+        if (e > end_all) e = end_all;
+        if (item_rows > 1) {
+            unsigned long long ie = (cur / item_rows + 1) * item_rows;
+            if (ie > row_end) ie = row_end;
+            if (e > ie) e = ie;
+        }
+        t1 = e;
+        cur = e;
+        return true;
+    }
+};
+
+template <class M, typename T, int NPL>
+__global__ void __launch_bounds__(PW_THREADS, (sizeof(typename M::Node) * NPL > 160 ? 1 : 2))
+pw_frontier_kernel(const PointwiseArgs a) {
+    using CT = typename M::CT;
+    constexpr int DIM = M::DIM;
+    constexpr int RB = DIM * (int) sizeof(T);
+    constexpr unsigned TILE_ROWS = PW_TILE_BYTES / RB;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* stage_base = smem;
+    double* red = reinterpret_cast<double*>(smem + PW_STAGES * PW_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + PW_RED_DOUBLES);
+    uint64_t* empty = full + PW_STAGES;
+    int* flag = reinterpret_cast<int*>(empty + PW_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned long long r0 = a.row_begin + (unsigned long long) blockIdx.x * a.rows_per_cta;
+    if (r0 > a.row_end) r0 = a.row_end;
+    unsigned long long r1 = r0 + a.rows_per_cta;
+    if (r1 > a.row_end) r1 = a.row_end;
+
+    if (tid == 0) {
+        for (int s = 0; s < PW_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], PW_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == PW_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+            unsigned long long t0, t1;
+            unsigned t = 0;
+            while (it.next(t0, t1)) {
+                const unsigned s = t % PW_STAGES;
+                if (t >= PW_STAGES) mbar_wait(&empty[s], ((t / PW_STAGES) - 1) & 1);
+                const unsigned long long b0 = t0 * RB, b1 = t1 * RB;
+                const unsigned long long w0 = b0 & ~15ull, w1 = (b1 + 15ull) & ~15ull;
+                const unsigned bytes = (unsigned) (w1 - w0);
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(stage_base + s * PW_STAGE_BYTES, static_cast<const unsigned char*>(a.data) + w0, bytes,
+                         &full[s]);
+                ++t;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const unsigned B = a.B;
+    unsigned NB = 32;  // node lanes (power of two >= min(B, 32))
+    if (B < 32) {
+        NB = 1;
+        while (NB < B) NB <<= 1;
+    }
+    const unsigned PL = 32 / NB;
+    const unsigned nb = lane & (NB - 1), pl = lane / NB;
+    const unsigned slot = warp * PL + pl, nslots = PW_CONSUMER_WARPS * PL;
+
+    typename M::Node nd[NPL];
+#pragma unroll
+    for (int n = 0; n < NPL; ++n) {
+        unsigned node = nb + 32 * n;
+        if (node >= B) node = B - 1;  // idle lanes shadow the last node; their sums are dropped
+        M::load(nd[n], a.theta + (size_t) node * a.theta_len, a.K);
+    }
+
+    double accS[NPL], accQ[NPL];
+#pragma unroll
+    for (int n = 0; n < NPL; ++n) accS[n] = accQ[n] = 0.0;
+
+    // owner-thread state (thread b < B assembles node b's item totals)
+    ItemOwner own;
+    own.init(r0, a.item_rows);
+
+    TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+    unsigned long long t0, t1;
+    unsigned t = 0;
+    while (it.next(t0, t1)) {
+        const unsigned s = t % PW_STAGES;
+        mbar_wait(&full[s], (t / PW_STAGES) & 1);
+        const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB) & 15ull);
+        const unsigned nrows = (unsigned) (t1 - t0);
+#pragma unroll 2
+        for (unsigned j = slot; j < nrows; j += nslots) {
+            CT x[DIM];
+            load_row<T, DIM, CT>(base + (size_t) j * RB, x);
+#pragma unroll
+            for (int n = 0; n < NPL; ++n) {
+                const double v = (double) M::rowlp(nd[n], x);
+                accS[n] += v;
+                if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+
+        if constexpr (!M::ITEM1) {
+            double* r = red + (t & 1) * (PW_CONSUMER_WARPS * kMaxNodesPerPass);
+#pragma unroll
+            for (int n = 0; n < NPL; ++n) {
+                double v = accS[n];
+                accS[n] = 0.0;
+                for (unsigned m = 16; m >= NB; m >>= 1) v += shfl_xor_f64(v, m);
+                if (pl == 0) r[warp * kMaxNodesPerPass + nb + 32 * n] = v;
+            }
+            named_bar_sync(1, PW_CONSUMERS);
+            if ((unsigned) tid < B) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < PW_CONSUMER_WARPS; ++w) tot += r[w * kMaxNodesPerPass + tid];
+                own.add_tile(tot, t1, a.item_rows, a.row_end);
+            }
+        }
+        ++t;
+    }
+
+    double* rec = a.part + (size_t) blockIdx.x * kPartSlots * kMaxNodesPerPass;
+    if constexpr (M::ITEM1) {
+        // one block reduction at the very end: every row is its own item
+#pragma unroll
+        for (int n = 0; n < NPL; ++n) {
+            double v = accS[n], q = accQ[n];
+            for (unsigned m = 16; m >= NB; m >>= 1) {
+                v += shfl_xor_f64(v, m);
+                q += shfl_xor_f64(q, m);
+            }
+            if (pl == 0) {
+                red[warp * kMaxNodesPerPass + nb + 32 * n] = v;
+                red[PW_CONSUMER_WARPS * kMaxNodesPerPass + warp * kMaxNodesPerPass + nb + 32 * n] = q;
+            }
+        }
+        named_bar_sync(1, PW_CONSUMERS);
+        if ((unsigned) tid < B) {
+#pragma unroll
+            for (int w = 0; w < PW_CONSUMER_WARPS; ++w) {
+                own.S += red[w * kMaxNodesPerPass + tid];
+                own.Q += red[PW_CONSUMER_WARPS * kMaxNodesPerPass + w * kMaxNodesPerPass + tid];
+            }
+        }
+    } else if ((unsigned) tid < B)
+        own.finish();
+    if ((unsigned) tid < B) {
+        own.store(rec, tid);
+        __threadfence();
+    }
+    named_bar_sync(1, PW_CONSUMERS);
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(a.ticket, 1u);
+        flag[0] = (prev == gridDim.x - 1);
+    }
+    named_bar_sync(1, PW_CONSUMERS);
+    if (!flag[0]) return;
+
+    // ---------------------------------------------------------------------- last CTA: finalize
+    __threadfence();
+    if ((unsigned) tid < B) {
+        double S, Q;
+        finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
+                       S, Q);
+        a.out[tid] = S;
+        a.out[B + tid] = Q;
+    }
+    if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
+}
+
+// scalar Boltzmann (boltzmannsampler.hh:71-82): x = -theta/T; sum = x*count; sum_sq = x*x*count
+__global__ void boltzmann_scalar_kernel(const double* theta, double* out, unsigned B, double count, double inv_t) {
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        const double x = -theta[b] * inv_t;
+        out[b] = x * count;
+        out[B + b] = x * x * count;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: dispatch
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr size_t kPwSmem = (size_t) PW_STAGES * PW_STAGE_BYTES + PW_RED_DOUBLES * sizeof(double) +
+                           2 * PW_STAGES * sizeof(uint64_t) + 16;
+
+template <class M, typename T, int NPL>
+int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
+    auto kern = pw_frontier_kernel<M, T, NPL>;
+    static bool configured_dev[64] = {};
+    static int occ_dev[64] = {};
+    bool& configured = configured_dev[e.device & 63];
+    int& occ = occ_dev[e.device & 63];
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kPwSmem);
+        if (err != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+            return -1;
+        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PW_THREADS, kPwSmem);
+        if (occ < 1) occ = 1;
+        if (occ > 2) occ = 2;
+        configured = true;
+    }
+    PointwiseArgs a = proto;
+    const unsigned long long rows = a.row_end - a.row_begin;
+    constexpr unsigned TILE_ROWS = PW_TILE_BYTES / (M::DIM * sizeof(T));
+    unsigned long long grid = (unsigned long long) e.sm_count * occ;
+    const unsigned long long tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    if (grid > tiles) grid = tiles;
+    if (grid > (unsigned long long) kMaxGrid) grid = kMaxGrid;
+    if (grid < 1) grid = 1;
+    a.rows_per_cta = (unsigned) ((rows + grid - 1) / grid);
+    grid = (rows + a.rows_per_cta - 1) / a.rows_per_cta;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned) grid, PW_THREADS, kPwSmem, s>>>(a);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("pointwise kernel launch: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 1;
+}
+
+template <class M, typename T>
+int launch_npl(Engine& e, const PointwiseArgs& a, cudaStream_t s, bool allow2) {
+    if (a.B > 32 && allow2) return launch_one<M, T, 2>(e, a, s);
+    return launch_one<M, T, 1>(e, a, s);
+}
+
+template <typename T>
+int dispatch_normal(Engine& e, const PointwiseArgs& a, cudaStream_t s, bool general) {
+#define PF_NORMAL_CASE(Dv)                                                                 \
+    case Dv:                                                                               \
+        return general ? launch_npl<NormalModel<Dv, T, true>, T>(e, a, s, Dv <= 2)         \
+                       : launch_npl<NormalModel<Dv, T, false>, T>(e, a, s, Dv <= 4);
+    switch (e.dim) {
+        PF_NORMAL_CASE(1)
+        PF_NORMAL_CASE(2)
+        PF_NORMAL_CASE(3)
+        PF_NORMAL_CASE(4)
+        PF_NORMAL_CASE(8)
+    }
+#undef PF_NORMAL_CASE
+    set_error("normal target: dimension %u not built (1,2,3,4,8)", e.dim);
+    return -1;
+}
+
+template <typename T>
+int dispatch_mixture(Engine& e, const PointwiseArgs& a, cudaStream_t s) {
+    if (e.K == 8 && e.dim == 2) return launch_npl<MixtureModel<8, 2, T>, T>(e, a, s, true);
+    if (e.K == 8 && e.dim == 8) return launch_npl<MixtureModel<8, 8, T>, T>(e, a, s, false);
+    switch (e.dim) {
+        case 1: return launch_npl<MixtureModelRT<1, T>, T>(e, a, s, true);
+        case 2: return launch_npl<MixtureModelRT<2, T>, T>(e, a, s, true);
+        case 3: return launch_npl<MixtureModelRT<3, T>, T>(e, a, s, true);
+        case 4: return launch_npl<MixtureModelRT<4, T>, T>(e, a, s, true);
+        case 8: return launch_npl<MixtureModelRT<8, T>, T>(e, a, s, true);
+    }
+    set_error("mixture: dimension %u not built (1,2,3,4,8)", e.dim);
+    return -1;
+}
+
+}  // namespace
+
+bool pointwise_supported(const Engine& e) {
+    const uint32_t d = e.dim;
+    return d == 1 || d == 2 || d == 3 || d == 4 || d == 8;
+}
+
+uint32_t pointwise_max_frontier(const Engine& e) {
+    if (e.desc.model == PF_MODEL_NORMAL) return e.dim <= 2 ? 64 : 32;  // general-covariance variant bound
+    if (e.desc.model == PF_MODEL_MIXTURE) return (e.K == 8 && e.dim == 8) ? 32 : 64;
+    return 64;
+}
+
+int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
+                     uint64_t n_items, cudaStream_t s) {
+    PointwiseArgs a{};
+    a.data = e.d_data;
+    a.theta = d_theta;
+    a.part = e.d_part;
+    a.out = d_out;
+    a.ticket = e.d_ticket;
+    a.item_rows = e.item_rows;
+    a.row_begin = first_item * e.item_rows;
+    a.row_end = (first_item + n_items) * e.item_rows;
+    if (a.row_end > e.n_rows) a.row_end = e.n_rows;
+    a.B = B;
+    a.theta_len = e.theta_len;
+    a.K = e.K;
+    if (a.row_end <= a.row_begin) {
+        cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
+        return 0;
+    }
+    if (e.desc.model == PF_MODEL_NORMAL) {
+        // The general-covariance variant reproduces the identity result exactly (W = I), so it is
+        // always correct; the identity fast path is chosen by the caller when every node's
+        // covariance is the identity (the only case the reference's proposals produce,
+        // normalsampler.hh:73-75).
+        const bool general = e.normal_general;
+        return e.f32 ? dispatch_normal<float>(e, a, s, general) : dispatch_normal<double>(e, a, s, general);
+    }
+    return e.f32 ? dispatch_mixture<float>(e, a, s) : dispatch_mixture<double>(e, a, s);
+}
+
+int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,
+                            cudaStream_t s) {
+    boltzmann_scalar_kernel<<<(B + 63) / 64, 64, 0, s>>>(d_theta, d_out, B, (double) n_items, 1.0 / e.temperature);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("boltzmann_scalar_kernel launch: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 1;
+}
+
+}  // namespace pf

@@ -1,0 +1,166 @@
+/* include/pfetch.h -- C ABI of the B200 frontier log-likelihood engine ("pfetch").
+ *
+ * This is the drop-in boundary for the evaluation path of elaine84/fetching.  In the
+ * reference every speculative tree node is shipped to an MPI worker, which walks the data
+ * set one item at a time through the Executor concept and accumulates two numbers:
+ *
+ *     worker.hh:148-155        log_prob = executor.evaluate(position);
+ *                              metric_sum += log_prob;  metric_sum_sq += log_prob * log_prob;
+ *
+ * and reports them in a MetricChange (protocol.hh:43-53).  Here the master hands the WHOLE
+ * speculative frontier (every JobInfo its scheduling burst produced, masterloop.cc:108-117)
+ * to pf_eval_frontier(), which scores all B nodes over all items in one pass of hand-written
+ * sm_100a kernels and returns, per node, exactly those two numbers.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status codes, no exceptions across
+ * the boundary, one calling thread per handle (every reference process is single threaded).
+ * Caller owns theta/result buffers; the engine owns its device copy of the data set.
+ *
+ * What each entry point replaces in the reference:
+ *   pf_engine_create       the data set every worker builds/holds for itself:
+ *                          samplers/normal.cc:38-48 (NormalSampler<2> over NDATA points),
+ *                          pysamplers/pymixture.py:57-64, pysamplers/pyblasso.py:44-69,
+ *                          samplers/python.cc:96-139 (set_arguments -> sampler(args))
+ *   pf_engine_data_size    the size_t a worker REGISTERs (worker.hh:66; python.cc:196-204;
+ *                          pymixture.py:66-67; pyblasso.py:79-80)
+ *   pf_eval_frontier       Executor::evaluate / evaluate_many over [0, data_size) for every
+ *                          frontier node: normalsampler.hh:128-165, boltzmannsampler.hh:71-82,
+ *                          python.cc:182-192 -> pymixture.py:86-92, pyblasso.py:135-141
+ *   pf_eval_frontier_range the same over items [first, first+count) -- the partial updates of
+ *                          worker.hh:141-162 (batch_size items per MetricChange)
+ *   pf_blasso_log_prior    python.cc:168-176 -> pyblasso.py:123-133
+ *   pf_engine_comm_init    nothing (the reference has no data parallelism): row
+ *                          shards of one data set on several GPUs, partial (sum, sum_sq)
+ *                          all-reduced with NCCL over NVLink
+ *
+ * THETA LAYOUT (doubles per node = pf_engine_theta_len()):
+ *   PF_MODEL_NORMAL           D means, then the packed lower-triangular covariance,
+ *                             D + D(D+1)/2 values (normaltheta.hh:24,49,81-87)
+ *   PF_MODEL_BOLTZMANN_SCALAR 1 value (boltzmannsampler.hh:31)
+ *   PF_MODEL_BOLTZMANN_DENSE  D unit states x (new workload; log p = -x'Wx/T, one item)
+ *   PF_MODEL_MIXTURE          K*d component means, row-major [K][d] (pymixture.py:72-73)
+ *   PF_MODEL_BLASSO           sigma, then p coefficients beta (pyblasso.py:138-139)
+ *
+ * ITEMS.  metric_sum_sq is a sum of squares of ITEM log-probabilities.  An item is one point
+ * for the normal target (normalsampler.hh:128-129), one batch of `item_rows` rows for the
+ * Python models (pymixture.py:86-92, pyblasso.py:135-141), the whole energy for Boltzmann.
+ */
+#ifndef PFETCH_H
+#define PFETCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PF_API __attribute__((visibility("default")))
+#else
+#define PF_API
+#endif
+
+typedef struct pf_engine pf_engine;
+
+enum pf_status {
+    PF_OK = 0,
+    PF_ERR_INVALID = -1,      /* bad argument (null pointer, B == 0, unknown model ...) */
+    PF_ERR_CUDA = -2,         /* a CUDA call failed; see pf_last_error() */
+    PF_ERR_SHAPE = -3,        /* sizes inconsistent with the model */
+    PF_ERR_NOMEM = -4,
+    PF_ERR_UNSUPPORTED = -5,  /* e.g. dimension outside what the kernels are built for */
+    PF_ERR_NCCL = -6,
+    PF_ERR_NO_DEVICE = -7     /* no sm_100 device: there is NO CPU fallback */
+};
+
+enum pf_model {
+    PF_MODEL_NORMAL = 1,            /* samplers/normal.cc, normalsampler.hh */
+    PF_MODEL_BOLTZMANN_SCALAR = 2,  /* boltzmannsampler.hh */
+    PF_MODEL_BOLTZMANN_DENSE = 3,   /* BASELINE config 2 (no reference implementation) */
+    PF_MODEL_MIXTURE = 4,           /* pysamplers/pymixture.py */
+    PF_MODEL_BLASSO = 5             /* pysamplers/pyblasso.py */
+};
+
+enum pf_dtype {
+    PF_F64 = 0, /* data stored and computed in IEEE double, like the reference (1e-10 rel) */
+    PF_F32 = 1  /* data stored/computed in float, FP64 accumulation (1e-5 rel) */
+};
+
+typedef struct pf_model_desc {
+    int32_t model;       /* enum pf_model */
+    int32_t dtype;       /* enum pf_dtype */
+    int32_t device;      /* CUDA device ordinal */
+    int32_t reserved;
+    uint64_t n_rows;     /* rows of `data` held by THIS engine (points / X rows / W rows);
+                            for BOLTZMANN_SCALAR: the item count (testmaster -d) */
+    uint32_t dim;        /* D (normal), d (mixture), p (lasso), D (dense Boltzmann) */
+    uint32_t components; /* K (mixture), else 0 */
+    uint64_t item_rows;  /* rows per item: 1 (normal), batch (mixture), 18000 (lasso), 0 = default */
+    uint64_t n_items;    /* items held by this engine; 0 = derive it the reference's way:
+                            n_rows (normal); (n_rows+1)/item_rows but whole items only (mixture,
+                            pymixture.py:64); n_rows/item_rows (lasso, pyblasso.py:69); 1 (dense) */
+    double param;        /* temperature T (Boltzmann, boltzmannsampler.hh:36-38; 0 -> 1.0) */
+    const double* data;  /* HOST, row-major [n_rows][dim] doubles; copied to the device once */
+    const double* response; /* HOST, lasso y[n_rows]; else NULL */
+} pf_model_desc;
+
+/* Create an engine; the data set is copied to device memory (converted to float for PF_F32)
+ * and stays resident.  For a row-sharded data set each rank passes only its own rows, cut at
+ * item boundaries.  Returns PF_OK or a negative pf_status. */
+PF_API int pf_engine_create(const pf_model_desc* desc, pf_engine** out);
+PF_API void pf_engine_destroy(pf_engine* e);
+
+PF_API uint64_t pf_engine_data_size(const pf_engine* e); /* items held by this engine */
+PF_API uint32_t pf_engine_theta_len(const pf_engine* e); /* doubles per node */
+PF_API uint32_t pf_engine_max_frontier(const pf_engine* e); /* nodes scored per kernel pass; larger B is chunked */
+
+/* Score B frontier nodes over ALL items.  thetas: HOST [B][theta_len]; sum, sum_sq: HOST [B]
+ * (overwritten).  Host->device copy of thetas, kernels, optional all-reduce, device->host copy
+ * of 2*B doubles, all on the engine's stream; returns when the results are in `sum`/`sum_sq`. */
+PF_API int pf_eval_frontier(pf_engine* e, uint32_t B, const double* thetas, double* sum, double* sum_sq);
+
+/* Same over items [first_item, first_item + n_items) only.  For PF_MODEL_NORMAL the items are
+ * visited in the reference's per-node pseudo-random order when `order` is non-NULL:
+ * order[2*b] = stride, order[2*b+1] = start of node b's StrideIndex (strideindex.hh:46-48,
+ * normalsampler.hh:115-119); NULL means natural order.  Results are the sums over the range
+ * (the caller adds them to its running MetricChange, worker.hh:130-134). */
+PF_API int pf_eval_frontier_range(pf_engine* e, uint32_t B, const double* thetas, uint64_t first_item,
+                           uint64_t n_items, const uint64_t* order, double* sum, double* sum_sq);
+
+/* Device-resident variant: d_thetas [B][theta_len] and d_out [2][B] (sums, then sums of
+ * squares) are DEVICE pointers; work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the
+ * engine's own stream) and the call returns without synchronising.  B <= pf_engine_max_frontier. */
+PF_API int pf_eval_frontier_device(pf_engine* e, uint32_t B, const double* d_thetas, double* d_out,
+                            void* cuda_stream);
+
+/* BLasso.log_prior (pyblasso.py:123-133): host-side, O(p); tau is the Laplace rate (5.0). */
+PF_API double pf_blasso_log_prior(const double* theta, uint32_t p, double tau);
+
+/* Row-sharded multi-GPU: one engine per rank over its shard; after pf_engine_comm_init the
+ * eval calls all-reduce (sum) the 2*B partials with NCCL so every rank gets the totals.
+ * pf_nccl_unique_id fills a 128-byte id on one rank; ship it to the others out of band. */
+PF_API int pf_nccl_unique_id(void* id128);
+PF_API int pf_engine_comm_init(pf_engine* e, const void* id128, int rank, int nranks);
+
+/* Options. */
+enum pf_option {
+    /* PF_MODEL_NORMAL, device-pointer path only: promise that every node's covariance is the
+     * identity (what the reference's proposals always produce, normalsampler.hh:73-75), which
+     * selects the cheaper kernel.  The host-pointer path inspects the thetas itself. */
+    PF_OPT_ASSUME_IDENTITY_COV = 1
+};
+PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
+
+/* Introspection. */
+PF_API int pf_abi_version(void);
+PF_API const char* pf_last_error(void);                 /* thread-local text of the last failure */
+PF_API uint64_t pf_engine_launch_count(const pf_engine* e); /* kernels launched by this engine so far */
+PF_API int pf_device_sm_count(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFETCH_H */

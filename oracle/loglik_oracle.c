@@ -355,9 +355,10 @@ void orc_boltzmann_scalar_eval(double theta, double temperature, size_t count, d
 
 /* NEW WORKLOAD (BASELINE config 2; no reference code).  Dense pairwise energy
  *   E(x) = x' W x,   log p(x) = -E(x)/T.
- * Item i (of D) is row i's share  e_i = -x_i * (W_i . x) / T, so that
- * metric_sum = sum_i e_i = -x'Wx/T and metric_sum_sq = sum_i e_i^2, mirroring how the
- * reference accumulates per-item terms (worker.hh:148-155). */
+ * The data set is ONE item, as the reference's Boltzmann plugin registers data_size = 1
+ * (samplers/boltzmann.cc:36): metric_sum = -x'Wx/T and metric_sum_sq = metric_sum^2.
+ * orc_boltzmann_dense_eval exposes the row terms e_i = -x_i (W_i . x)/T (and their squares)
+ * as a building block; orc_boltzmann_dense_logp is the item value the engine must return. */
 void orc_boltzmann_dense_eval(const double* W, size_t D, const double* x, double temperature,
                               size_t first, size_t count, double* sum, double* sum_sq) {
     double s = *sum, q = *sum_sq;
@@ -605,14 +606,19 @@ void orc_normal_frontier_mt(const double* data, size_t n, int D, const double* t
     }
 }
 
+double orc_boltzmann_dense_logp(const double* W, size_t D, const double* x, double temperature) {
+    double s = 0, q = 0;
+    orc_boltzmann_dense_eval(W, D, x, temperature, 0, D, &s, &q);
+    return s;
+}
+
 void orc_boltzmann_dense_frontier_mt(const double* W, size_t D, const double* X, size_t nodes,
                                      double temperature, double* sum, double* sum_sq) {
 #pragma omp parallel for schedule(dynamic, 1)
     for (size_t b = 0; b < nodes; ++b) {
-        double s = 0, q = 0;
-        orc_boltzmann_dense_eval(W, D, X + b * D, temperature, 0, D, &s, &q);
-        sum[b] = s;
-        sum_sq[b] = q;
+        double lp = orc_boltzmann_dense_logp(W, D, X + b * D, temperature);
+        sum[b] = lp;          /* one item: worker.hh:151-152 with a single evaluate() */
+        sum_sq[b] = lp * lp;
     }
 }
 

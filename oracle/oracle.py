@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.orc_mixture_frontier_mt.argtypes = [_dp, sz, C.c_int, C.c_int, _dp, sz, sz, sz, _dp, _dp]
         L.orc_blasso_frontier_mt.argtypes = [_dp, _dp, sz, C.c_int, _dp, sz, sz, sz, _dp, _dp]
         L.orc_normal_frontier_mt.argtypes = [_dp, sz, C.c_int, _dp, sz, _dp, _dp]
+        L.orc_boltzmann_dense_logp.argtypes = [_dp, sz, _dp, C.c_double]
+        L.orc_boltzmann_dense_logp.restype = C.c_double
         L.orc_boltzmann_dense_frontier_mt.argtypes = [_dp, sz, _dp, sz, C.c_double, _dp, _dp]
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -154,6 +156,12 @@ def boltzmann_dense_eval(W, x, temperature=1.0, first=0, count=None):
     s, q = C.c_double(0), C.c_double(0)
     lib().orc_boltzmann_dense_eval(_p(W), D, _p(x), temperature, first, count, C.byref(s), C.byref(q))
     return s.value, q.value
+
+
+def boltzmann_dense_logp(W, x, temperature=1.0):
+    """The single item value: -x'Wx/T."""
+    W, x = _c(W), _c(x)
+    return float(lib().orc_boltzmann_dense_logp(_p(W), W.shape[0], _p(x), temperature))
 
 
 def boltzmann_dense_eval_ld(W, x, temperature=1.0):

@@ -138,6 +138,9 @@ def test_dense_boltzmann_definition(orc):
     assert rel(s, -(x @ W @ x) / 2.0) < 1e-12
     sl, ql = orc.boltzmann_dense_eval_ld(W, x, 2.0)
     assert rel(float(sl), s) < 1e-12 and rel(float(ql), q) < 1e-12
+    assert orc.boltzmann_dense_logp(W, x, 2.0) == s
+    S, Q = orc.boltzmann_dense_frontier(W, np.stack([x, 2 * x]), 2.0)
+    assert S[0] == s and Q[0] == s * s and rel(S[1], 4 * s) < 1e-14
     s1, q1 = orc.boltzmann_dense_eval(W, x, 2.0, 0, 10)
     s2, q2 = orc.boltzmann_dense_eval(W, x, 2.0, 10, D - 10)
     assert rel(s1 + s2, s) < 1e-12 and rel(q1 + q2, q) < 1e-12
