@@ -301,7 +301,9 @@ def main():
         eng.comm_init(ids[0], rank, world)
     shard.pop("data")  # the engine owns the device copy; free the host rows
 
-    stream = torch.cuda.current_stream()
+    # an explicit stream: handle 0 (the legacy default stream) means "the engine's own stream" in the C ABI
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     d_th = torch.from_numpy(thetas).cuda()
     d_out = torch.zeros(2, B, dtype=torch.float64, device="cuda")
 

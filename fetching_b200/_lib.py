@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libpfetch.so")
+LIB_PATH = os.environ.get("PFETCH_LIB") or os.path.join(PKG, "lib", "libpfetch.so")  # PFETCH_LIB: experimental variants
 
 PF_OK = 0
 STATUS = {0: "PF_OK", -1: "PF_ERR_INVALID", -2: "PF_ERR_CUDA", -3: "PF_ERR_SHAPE", -4: "PF_ERR_NOMEM",
@@ -50,6 +50,7 @@ SYMBOLS = {
     "pf_last_error": (C.c_char_p, []),
     "pf_engine_launch_count": (C.c_uint64, [C.c_void_p]),
     "pf_device_sm_count": (C.c_int, [C.c_int]),
+    "pf_debug_math": (C.c_int, [C.c_int, _dp, _dp, C.c_size_t, C.c_int]),
 }
 
 _lib = None

@@ -49,11 +49,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
+    """`out` / `defines` build an experimental variant next to the default library (PFETCH_LIB selects it)."""
+    if out == LIB and not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" if out == LIB else "obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)
@@ -64,27 +65,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in CU_SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ccbin, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode != 0:
-            print(out)
+            print(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
     host_cpp = sorted(os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))
                       if f.endswith(".cpp")) if os.path.isdir(os.path.join(CSRC, "host")) else []
     link = [nvcc, *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17",
             "-Xcompiler", "-fPIC,-O2", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-            "-o", LIB, *objs, *host_cpp, "-lcuda", "-ldl"]
+            "-o", out, *objs, *host_cpp, "-lcuda", "-ldl"]
     if verbose:
         print(" ".join(link), flush=True)
     subprocess.run(link, check=True, env=env)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                out=os.path.join(LIBDIR, outs[0]) if outs else LIB, defines=defs))

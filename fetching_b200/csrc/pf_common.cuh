@@ -146,39 +146,67 @@ struct ItemOwner {
     }
 };
 
+// Finalize, run by the 256 consumer threads of the LAST CTA to finish.  Thread t works for node
+// (t mod BP) as worker (t / BP): it folds the records of CTAs worker, worker+NW, ... -- plain S/Q
+// sums plus, for every CTA in which a cut item ENDS, that item's stitched total
+//     tail(first CTA of the item) + head(next CTA) + ... + head(this CTA)
+// whose CTA span is known analytically, so all loads are independent (no serial carry chain) --
+// and the NW workers are then combined in worker order.  Fixed order => bit-stable.
+// `nthreads` consumer threads take part (tid < nthreads); `scratch` holds 2 * nthreads doubles.
+// Returns S/Q to threads tid < B.
 __device__ __forceinline__ void finalize_items(const double* part, unsigned grid, unsigned long long row_begin,
                                                unsigned long long row_end, unsigned long long rows_per_cta,
-                                               unsigned long long item_rows, unsigned tid, double& S_out,
+                                               unsigned long long item_rows, unsigned tid, unsigned B,
+                                               double* scratch, int bar_id, unsigned nthreads, double& S_out,
                                                double& Q_out) {
-    double S = 0.0, Q = 0.0, carry = 0.0;
-    for (unsigned c = 0; c < grid; ++c) {
-        unsigned long long c0 = row_begin + (unsigned long long) c * rows_per_cta;
-        if (c0 >= row_end) break;
-        unsigned long long c1 = c0 + rows_per_cta;
-        if (c1 > row_end) c1 = row_end;
-        const double* pr = part + (size_t) c * 4 * kMaxNodesPerPass + tid;
-        if (item_rows <= 1) {
-            S += ld_cg_f64(pr);
-            Q += ld_cg_f64(pr + kMaxNodesPerPass);
-            continue;
-        }
-        const bool head_open = (c0 % item_rows) != 0;
-        if (head_open) {
-            carry += ld_cg_f64(pr + 2 * kMaxNodesPerPass);
-            unsigned long long ie = (c0 / item_rows + 1) * item_rows;
-            if (ie > row_end) ie = row_end;
-            if (ie <= c1) {  // the cut item ends inside this CTA
-                S += carry;
-                Q = fma(carry, carry, Q);
-                carry = 0.0;
-            }
-        }
+    unsigned BP = 64;
+    if (B <= 32) {
+        BP = 1;
+        while (BP < B) BP <<= 1;
+    }
+    const unsigned NW = nthreads / BP;  // workers per node; threads beyond NW * BP idle
+    const unsigned b = tid % BP, worker = tid / BP;
+    const unsigned bb = b < B ? b : B - 1;
+    double S = 0.0, Q = 0.0;
+    unsigned gmax = grid;  // rows_per_cta == 0: every launched CTA wrote a plain (S, Q) record
+    if (rows_per_cta) {
+        const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
+        if (n_cta < gmax) gmax = (unsigned) n_cta;
+    }
+#pragma unroll 4
+    for (unsigned c = worker < NW ? worker : gmax; c < gmax; c += NW) {
+        const double* pr = part + (size_t) c * 4 * kMaxNodesPerPass + bb;
         S += ld_cg_f64(pr);
         Q += ld_cg_f64(pr + kMaxNodesPerPass);
-        const unsigned long long ls = ((c1 - 1) / item_rows) * item_rows;
-        unsigned long long le = ls + item_rows;
-        if (le > row_end) le = row_end;
-        if (le > c1 && ls >= c0 && (ls > c0 || !head_open)) carry = ld_cg_f64(pr + 3 * kMaxNodesPerPass);
+        if (item_rows > 1) {
+            const unsigned long long c0 = row_begin + (unsigned long long) c * rows_per_cta;
+            unsigned long long c1 = c0 + rows_per_cta;
+            if (c1 > row_end) c1 = row_end;
+            const unsigned long long q0 = c0 / item_rows;
+            if (c0 != q0 * item_rows) {  // an item begun earlier reaches into this CTA
+                unsigned long long ie = (q0 + 1) * item_rows;
+                if (ie > row_end) ie = row_end;
+                if (ie <= c1) {  // ... and ends here: stitch it
+                    const unsigned cs = (unsigned) ((q0 * item_rows - row_begin) / rows_per_cta);
+                    double tot = ld_cg_f64(part + (size_t) cs * 4 * kMaxNodesPerPass + 3 * kMaxNodesPerPass + bb);
+                    for (unsigned k = cs + 1; k <= c; ++k)
+                        tot += ld_cg_f64(part + (size_t) k * 4 * kMaxNodesPerPass + 2 * kMaxNodesPerPass + bb);
+                    S += tot;
+                    Q = fma(tot, tot, Q);
+                }
+            }
+        }
+    }
+    scratch[tid] = S;
+    scratch[nthreads + tid] = Q;
+    named_bar_sync(bar_id, (int) nthreads);
+    S = 0.0;
+    Q = 0.0;
+    if (tid < B) {
+        for (unsigned w = 0; w < NW; ++w) {
+            S += scratch[w * BP + tid];
+            Q += scratch[nthreads + w * BP + tid];
+        }
     }
     S_out = S;
     Q_out = Q;

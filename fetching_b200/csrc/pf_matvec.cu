@@ -283,19 +283,20 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     if (!flag[0]) return;
 
     __threadfence();
-    if ((unsigned) tid < B) {
-        if constexpr (BOLTZ) {
-            double E = 0.0;
-            for (unsigned c = 0; c < gridDim.x; ++c)
-                E += ld_cg_f64(a.part + (size_t) c * kPartSlots * kMaxNodesPerPass + tid);
-            const double lp = -E * a.inv_temperature;  // one item: the whole energy
-            a.out[tid] = lp;
-            a.out[B + tid] = lp * lp;
-        } else {
-            double S, Q;
-            finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows, tid, S, Q);
-            a.out[tid] = S;
-            a.out[B + tid] = Q;
+    {
+        // Boltzmann: the records hold plain energy partials (one item): finalize with item_rows = 1
+        double S, Q;
+        finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
+                       BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q);
+        if ((unsigned) tid < B) {
+            if constexpr (BOLTZ) {
+                const double lp = -S * a.inv_temperature;  // one item: the whole energy
+                a.out[tid] = lp;
+                a.out[B + tid] = lp * lp;
+            } else {
+                a.out[tid] = S;
+                a.out[B + tid] = Q;
+            }
         }
     }
     if (tid == 0) *a.ticket = 0u;
@@ -358,6 +359,9 @@ int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
     static bool configured_dev[64] = {};
     if (!configured_dev[e.device & 63]) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMvSmem);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) {
             set_error("cudaFuncSetAttribute(matvec): %s", cudaGetErrorString(err));
             return -1;

@@ -27,10 +27,11 @@
 
 #include "pf_common.cuh"
 #include "pf_engine.h"
+#include "pf_math.cuh"
 
 namespace pf {
 
-constexpr int PW_CONSUMER_WARPS = 8;
+constexpr int PW_CONSUMER_WARPS = 7;  // + 1 producer warp = 256 threads: two CTAs per SM fit at up to 128 registers
 constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
 constexpr int PW_THREADS = PW_CONSUMERS + 32;  // + one producer warp
 constexpr int PW_STAGES = 4;
@@ -42,10 +43,6 @@ constexpr double kLog2Pi = 1.837877066409345483560659472810;  // normalsampler.h
 template <typename T> struct ComputeOf { using type = double; };
 template <> struct ComputeOf<float> { using type = float; };
 
-__device__ __forceinline__ double pf_exp(double x) { return exp(x); }
-__device__ __forceinline__ float pf_exp(float x) { return expf(x); }
-__device__ __forceinline__ double pf_log(double x) { return log(x); }
-__device__ __forceinline__ float pf_log(float x) { return logf(x); }
 
 // ---------------------------------------------------------------------------------------------
 // row loader: DIM values of T from shared memory (alignment = gcd(16, DIM*sizeof(T)))
@@ -79,6 +76,7 @@ template <int D, typename T, bool GENERAL>
 struct NormalModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = true;
+    static constexpr bool THETA_IN_SMEM = false;
     using CT = typename ComputeOf<T>::type;
     struct Node {
         CT mu[D];
@@ -156,47 +154,91 @@ struct NormalModel {
 // Gaussian mixture with unit-variance spherical components, unnormalised (pymixture.py:86-92).
 // The reference multiplies d one-dimensional exps per component; exp of the summed exponent is
 // the same number to rounding (<= d ulp) and costs one exp instead of d.
+//
+// theta lives in a padded shared-memory copy ([node][K*D + pad], pad chosen so that the node rows
+// start 16 bytes apart modulo 128: conflict-free LDS.128 for up to 8 nodes per warp-load), NOT in
+// registers: the registers go to G interleaved exp chains per lane, which is what keeps the FP64
+// pipe fed (a single dependent DFMA chain only issues once per pipe latency).
+template <typename CT>
+__host__ __device__ constexpr unsigned theta_smem_stride(unsigned theta_len) {
+    // elements; rows start (stride * sizeof(CT)) apart: make that == 16 (mod 128) bytes
+    const unsigned per16 = 16 / (unsigned) sizeof(CT);
+    unsigned s = (theta_len + per16 - 1) / per16 * per16;
+    while ((s * (unsigned) sizeof(CT)) % 128 != 16) s += per16;
+    return s;
+}
+
 template <int K, int D, typename T>
 struct MixtureModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = false;
+    static constexpr bool THETA_IN_SMEM = true;
     using CT = typename ComputeOf<T>::type;
     struct Node {
-        CT th[K * D];
+        const CT* th;
+        const double* tab;  // 2^(j/32) in shared memory
     };
-    static __device__ void load(Node& nd, const double* th, unsigned) {
-#pragma unroll
-        for (int i = 0; i < K * D; ++i) nd.th[i] = (CT) th[i];
+    static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab) {
+        nd.th = th_smem;
+        nd.tab = tab;
     }
-    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
-        CT lp = 0;
-#pragma unroll
+    // library exp/log: subnormal terms, log(0) = -inf, nan propagation exactly like numpy's
+    static __device__ __noinline__ CT slow(const CT* th, const CT (&x)[D]) {
+        double lp = 0;
         for (int k = 0; k < K; ++k) {
-            CT e = 0;
-#pragma unroll
+            double e = 0;
             for (int j = 0; j < D; ++j) {
-                CT t = nd.th[k * D + j] - x[j];
+                const double t = (double) th[k * D + j] - (double) x[j];
                 e = fma(t, t, e);
             }
-            lp += pf_exp((CT) -0.5 * e);
+            lp += exp(-0.5 * e);
         }
-        return pf_log(lp);
+        return (CT) log(lp);
+    }
+    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+        // exp chains kept in flight per lane (bounded by the registers the row operands need)
+        constexpr int GMAX = D <= 2 ? 8 : (D <= 4 ? 4 : 2);
+        constexpr int G = (K % GMAX == 0) ? GMAX : ((K % 2 == 0) ? 2 : 1);
+        CT lp = 0;
+#pragma unroll
+        for (int k0 = 0; k0 < K; k0 += G) {
+            CT e[G], v[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                CT th[D];
+                load_row<CT, D, CT>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), th);
+                e[g] = 0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const CT t = th[j] - x[j];
+                    e[g] = fma(t, t, e[g]);
+                }
+            }
+            exp_neg_half_fast_batch<G>(e, v, nd.tab);
+#pragma unroll
+            for (int g = 0; g < G; ++g) lp += v[g];
+        }
+        if (needs_slow_path(lp)) return slow(nd.th, x);  // every component ~40 sigma away, or non-finite input
+        return log_pos_fast(lp);
     }
 };
 
-// Any K (<= 32): theta stays in global/L1 (read-only, broadcast across point-lanes).  Fallback
-// for shapes without a register-resident instantiation.
+// Any K (<= 32): same, with a run-time component loop.  Fallback for shapes without a K-unrolled
+// instantiation.
 template <int D, typename T>
 struct MixtureModelRT {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = false;
+    static constexpr bool THETA_IN_SMEM = true;
     using CT = typename ComputeOf<T>::type;
     struct Node {
-        const double* th;
+        const CT* th;
+        const double* tab;
         unsigned K;
     };
-    static __device__ void load(Node& nd, const double* th, unsigned K) {
-        nd.th = th;
+    static __device__ void load(Node& nd, const CT* th_smem, unsigned K, const double* tab) {
+        nd.th = th_smem;
+        nd.tab = tab;
         nd.K = K;
     }
     static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
@@ -205,12 +247,24 @@ struct MixtureModelRT {
             CT e = 0;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                CT t = (CT) __ldg(&nd.th[k * D + j]) - x[j];
+                const CT t = nd.th[k * D + j] - x[j];
                 e = fma(t, t, e);
             }
-            lp += pf_exp((CT) -0.5 * e);
+            lp += exp_neg_half_fast(e, nd.tab);
         }
-        return pf_log(lp);
+        if (needs_slow_path(lp)) {
+            double l2 = 0;
+            for (unsigned k = 0; k < nd.K; ++k) {
+                double e = 0;
+                for (int j = 0; j < D; ++j) {
+                    const double t = (double) nd.th[k * D + j] - (double) x[j];
+                    e = fma(t, t, e);
+                }
+                l2 += exp(-0.5 * e);
+            }
+            return (CT) log(l2);
+        }
+        return log_pos_fast(lp);
     }
 };
 
@@ -236,9 +290,29 @@ struct TileIter {
     }
 };
 
+// Register budget: 256 threads per CTA, so two CTAs per SM fit at up to 128 registers per thread
+// (registers are granted per pair of warps: 2 x 8 x 32 x 128 = 64K).  Models whose per-lane
+// state is large get the whole register file of one CTA instead.
+template <class M, int NPL>
+constexpr bool pw_two_ctas() {
+    return sizeof(typename M::Node) * NPL <= 160;
+}
+
 template <class M, typename T, int NPL>
-__global__ void __launch_bounds__(PW_THREADS, (sizeof(typename M::Node) * NPL > 160 ? 1 : 2))
-pw_frontier_kernel(const PointwiseArgs a) {
+__device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a);
+
+template <class M, typename T, int NPL>
+__global__ void __launch_bounds__(PW_THREADS, 2) pw_frontier_kernel2(const PointwiseArgs a) {
+    pw_frontier_body<M, T, NPL>(a);
+}
+
+template <class M, typename T, int NPL>
+__global__ void __launch_bounds__(PW_THREADS, 1) pw_frontier_kernel1(const PointwiseArgs a) {
+    pw_frontier_body<M, T, NPL>(a);
+}
+
+template <class M, typename T, int NPL>
+__device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     using CT = typename M::CT;
     constexpr int DIM = M::DIM;
     constexpr int RB = DIM * (int) sizeof(T);
@@ -250,6 +324,7 @@ pw_frontier_kernel(const PointwiseArgs a) {
     uint64_t* full = reinterpret_cast<uint64_t*>(red + PW_RED_DOUBLES);
     uint64_t* empty = full + PW_STAGES;
     int* flag = reinterpret_cast<int*>(empty + PW_STAGES);
+    CT* th_smem = reinterpret_cast<CT*>(reinterpret_cast<unsigned char*>(flag) + 16);  // 16-byte aligned
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned long long r0 = a.row_begin + (unsigned long long) blockIdx.x * a.rows_per_cta;
@@ -299,11 +374,28 @@ pw_frontier_kernel(const PointwiseArgs a) {
     const unsigned slot = warp * PL + pl, nslots = PW_CONSUMER_WARPS * PL;
 
     typename M::Node nd[NPL];
+    if constexpr (M::THETA_IN_SMEM) {
+        __shared__ double exp2_tab[32];
+        if (tid < 32) exp2_tab[tid] = kExp2Tab[tid];
+        const unsigned stride = theta_smem_stride<CT>(a.theta_len);
+        for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
+            const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
+            th_smem[node * stride + j] = (CT) a.theta[i];
+        }
+        named_bar_sync(1, PW_CONSUMERS);
 #pragma unroll
-    for (int n = 0; n < NPL; ++n) {
-        unsigned node = nb + 32 * n;
-        if (node >= B) node = B - 1;  // idle lanes shadow the last node; their sums are dropped
-        M::load(nd[n], a.theta + (size_t) node * a.theta_len, a.K);
+        for (int n = 0; n < NPL; ++n) {
+            unsigned node = nb + 32 * n;
+            if (node >= B) node = B - 1;  // idle lanes shadow the last node; their sums are dropped
+            M::load(nd[n], th_smem + node * stride, a.K, exp2_tab);
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < NPL; ++n) {
+            unsigned node = nb + 32 * n;
+            if (node >= B) node = B - 1;
+            M::load(nd[n], a.theta + (size_t) node * a.theta_len, a.K);
+        }
     }
 
     double accS[NPL], accQ[NPL];
@@ -322,7 +414,7 @@ pw_frontier_kernel(const PointwiseArgs a) {
         mbar_wait(&full[s], (t / PW_STAGES) & 1);
         const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB) & 15ull);
         const unsigned nrows = (unsigned) (t1 - t0);
-#pragma unroll 2
+#pragma unroll(M::ITEM1 ? 2 : 1)
         for (unsigned j = slot; j < nrows; j += nslots) {
             CT x[DIM];
             load_row<T, DIM, CT>(base + (size_t) j * RB, x);
@@ -395,12 +487,14 @@ pw_frontier_kernel(const PointwiseArgs a) {
 
     // ---------------------------------------------------------------------- last CTA: finalize
     __threadfence();
-    if ((unsigned) tid < B) {
+    {
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
-                       S, Q);
-        a.out[tid] = S;
-        a.out[B + tid] = Q;
+                       B, red, 1, PW_CONSUMERS, S, Q);
+        if ((unsigned) tid < B) {
+            a.out[tid] = S;
+            a.out[B + tid] = Q;
+        }
     }
     if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
 }
@@ -415,23 +509,56 @@ __global__ void boltzmann_scalar_kernel(const double* theta, double* out, unsign
     }
 }
 
+// diagnostics: apply the transcendental kernels elementwise (tests/test_gpu_math.py)
+__global__ void debug_math_kernel(int which, const double* in, double* out, size_t n) {
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __syncthreads();
+    if (i >= n) return;
+    const double x = in[i];
+    double r;
+    switch (which) {
+        case 0: r = exp_neg_half(x, tab); break;
+        case 1: r = log_pos(x); break;
+        case 2: r = (double) exp_neg_half((float) x, tab); break;
+        default: r = (double) log_pos((float) x); break;
+    }
+    out[i] = r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: dispatch
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr size_t kPwSmem = (size_t) PW_STAGES * PW_STAGE_BYTES + PW_RED_DOUBLES * sizeof(double) +
-                           2 * PW_STAGES * sizeof(uint64_t) + 16;
+constexpr size_t kPwSmemBase = (size_t) PW_STAGES * PW_STAGE_BYTES + PW_RED_DOUBLES * sizeof(double) +
+                               2 * PW_STAGES * sizeof(uint64_t) + 32;
+
+template <class M>
+size_t pw_smem_bytes(unsigned theta_len, unsigned max_nodes) {
+    if (!M::THETA_IN_SMEM) return kPwSmemBase;
+    return kPwSmemBase + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
+}
 
 template <class M, typename T, int NPL>
 int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
-    auto kern = pw_frontier_kernel<M, T, NPL>;
+    void (*kern)(const PointwiseArgs);
+    if constexpr (pw_two_ctas<M, NPL>())
+        kern = pw_frontier_kernel2<M, T, NPL>;
+    else
+        kern = pw_frontier_kernel1<M, T, NPL>;
     static bool configured_dev[64] = {};
     static int occ_dev[64] = {};
     bool& configured = configured_dev[e.device & 63];
     int& occ = occ_dev[e.device & 63];
+    // theta staging area sized for a full pass (32 * NPL nodes) so the occupancy is B-independent
+    const size_t kPwSmem = pw_smem_bytes<M>(e.theta_len, 32 * NPL);
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kPwSmem);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) {
             set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
             return -1;
@@ -555,3 +682,15 @@ int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double
 }
 
 }  // namespace pf
+
+extern "C" PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int device) {
+    if (!in || !out || cudaSetDevice(device) != cudaSuccess) return PF_ERR_INVALID;
+    double *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, n * 8) != cudaSuccess || cudaMalloc(&d_out, n * 8) != cudaSuccess) return PF_ERR_NOMEM;
+    cudaMemcpy(d_in, in, n * 8, cudaMemcpyHostToDevice);
+    pf::debug_math_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(which, d_in, d_out, n);
+    cudaError_t err = cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return err == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+}

@@ -159,6 +159,9 @@ PF_API int pf_abi_version(void);
 PF_API const char* pf_last_error(void);                 /* thread-local text of the last failure */
 PF_API uint64_t pf_engine_launch_count(const pf_engine* e); /* kernels launched by this engine so far */
 PF_API int pf_device_sm_count(int device);
+/* Diagnostics: apply the engine's device exp(-x/2) (which = 0: double, 2: float) or log(x)
+ * (1: double, 3: float) elementwise to a HOST array, for accuracy tests of the math kernels. */
+PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int device);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,55 @@
+"""Accuracy of the engine's own exp/log device kernels (fetching_b200/csrc/pf_math.cuh)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run(which, x):
+    from fetching_b200 import _lib
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    _lib.check(lib.pf_debug_math(which, x.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size, 0), "pf_debug_math")
+    return out
+
+
+def test_exp_neg_half_fp64():
+    rng = np.random.RandomState(0)
+    e = np.concatenate([rng.uniform(0, 60, 200000), rng.uniform(0, 1500, 100000), 10.0 ** rng.uniform(-12, 1, 50000),
+                        [0.0, 1e-300, 1415.0, 1416.0, 1417.0, 1480.0, 1490.0, 1500.0, 3000.0, np.inf]])
+    got = run(0, e)
+    want = np.exp(-0.5 * e)
+    normal = want > 1e-300
+    rel = np.abs(got[normal] - want[normal]) / want[normal]
+    # |z| * 2^-53 argument rounding on top of ~1 ulp: < 5e-14 even at the underflow edge, < 4e-16 for e < 60
+    assert rel.max() < 5e-14
+    assert rel[e[normal] < 60].max() < 8e-15  # |z| <= 43 -> 43 * 2^-52 * ln2
+    assert np.all(np.abs(got[~normal] - want[~normal]) <= 1e-300)
+    assert got[-1] == 0.0 and got[-2] == 0.0
+
+
+def test_log_pos_fp64():
+    rng = np.random.RandomState(1)
+    x = np.concatenate([rng.uniform(1e-3, 8.0, 200000), 10.0 ** rng.uniform(-300, 300, 100000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 50000), [1.0, 2.0, 0.5, np.sqrt(2), 1 / np.sqrt(2), 1e-310, 0.0]])
+    got = run(1, x)
+    with np.errstate(divide="ignore"):
+        want = np.log(x)
+    fin = np.isfinite(want) & (want != 0)
+    err = np.abs(got[fin] - want[fin])
+    assert (err / np.maximum(np.abs(want[fin]), 1e-300)).max() < 1e-15 or (err / np.spacing(np.abs(want[fin]))).max() <= 4
+    assert got[-1] == -np.inf and got[-7] == 0.0
+
+
+def test_fp32_variants():
+    rng = np.random.RandomState(2)
+    e = rng.uniform(0, 80, 100000)
+    got = run(2, e)
+    want = np.exp(-0.5 * e)
+    assert (np.abs(got - want) / want).max() < 2e-5
+    x = rng.uniform(1e-3, 8.0, 100000)
+    assert np.abs(run(3, x) - np.log(x)).max() < 2e-6
