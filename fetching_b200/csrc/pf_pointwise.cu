@@ -216,7 +216,10 @@ struct MixtureModel {
             }
             exp_neg_half_fast_batch<G>(e, v, nd.tab);
 #pragma unroll
-            for (int g = 0; g < G; ++g) lp += v[g];
+            for (int w = 1; w < G; w *= 2)  // pairwise: depth log2(G) instead of G dependent adds
+#pragma unroll
+                for (int g = 0; g + w < G; g += 2 * w) v[g] += v[g + w];
+            lp += v[0];
         }
         if (needs_slow_path(lp)) return slow(nd.th, x);  // every component ~40 sigma away, or non-finite input
         return log_pos_fast(lp);
@@ -375,8 +378,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 
     typename M::Node nd[NPL];
     if constexpr (M::THETA_IN_SMEM) {
-        __shared__ double exp2_tab[32];
-        if (tid < 32) exp2_tab[tid] = kExp2Tab[tid];
+        __shared__ __align__(16) double exp2_tab[kExp2TabSize];
+        for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
         for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
@@ -512,8 +515,8 @@ __global__ void boltzmann_scalar_kernel(const double* theta, double* out, unsign
 // diagnostics: apply the transcendental kernels elementwise (tests/test_gpu_math.py)
 __global__ void debug_math_kernel(int which, const double* in, double* out, size_t n) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    __shared__ double tab[32];
-    if (threadIdx.x < 32) tab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __shared__ double tab[kExp2TabSize];
+    for (int i = threadIdx.x; i < kExp2TabSize; i += blockDim.x) tab[i] = kExp2Tab[i];
     __syncthreads();
     if (i >= n) return;
     const double x = in[i];

@@ -162,6 +162,10 @@ PF_API int pf_device_sm_count(int device);
 /* Diagnostics: apply the engine's device exp(-x/2) (which = 0: double, 2: float) or log(x)
  * (1: double, 3: float) elementwise to a HOST array, for accuracy tests of the math kernels. */
 PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int device);
+/* Diagnostics: measured FP64 FMA throughput (1e12 FMA/s) for warps/SM in {4,8,16,32} x
+ * independent chains per thread in {1,2,4,8}; out16[4*w + i].  The largest entry is the FP64
+ * roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
+PF_API int pf_debug_fp64_probe(int device, double* out16);
 
 #ifdef __cplusplus
 }

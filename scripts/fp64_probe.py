@@ -1,0 +1,10 @@
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, '.')
+from fetching_b200 import _lib
+lib = _lib.load()
+out = np.zeros(16)
+_lib.check(lib.pf_debug_fp64_probe(0, out.ctypes.data_as(C.POINTER(C.c_double))), "probe")
+print("TFMA/s (x2 = TFLOP/s); rows: warps/SM 4,8,16,32; cols: ILP 1,2,4,8")
+print(np.round(out.reshape(4, 4), 3))
+clk = 1.965e9; sms = 148
+print("FMA/clk/SM:"); print(np.round(out.reshape(4,4) * 1e12 / clk / sms, 2))
