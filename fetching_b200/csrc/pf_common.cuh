@@ -82,6 +82,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// non-blocking arrival on a named barrier (the matching waiters use named_bar_sync)
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_xor_sync(0xffffffffu, lo, mask);

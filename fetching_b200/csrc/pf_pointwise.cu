@@ -37,7 +37,10 @@ constexpr int PW_THREADS = PW_CONSUMERS + 32;  // + one producer warp
 constexpr int PW_STAGES = 4;
 constexpr int PW_TILE_BYTES = 16384;
 constexpr int PW_STAGE_BYTES = PW_TILE_BYTES + 32;  // room for the 16-byte aligned copy window
-constexpr int PW_RED_DOUBLES = 2 * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+constexpr int PW_RED_BUFS = 4;  // == PW_STAGES: a warp can never lead the owner warp by more than 3 tiles
+constexpr int PW_RED_DOUBLES = PW_RED_BUFS * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+constexpr int PW_BAR_TILE0 = 1;  // named barriers 1..4: per-tile partials ready; 5: CTA-wide among consumers
+constexpr int PW_BAR_ALL = 5;
 constexpr double kLog2Pi = 1.837877066409345483560659472810;  // normalsampler.hh:24-26
 
 template <typename T> struct ComputeOf { using type = double; };
@@ -385,7 +388,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
             th_smem[node * stride + j] = (CT) a.theta[i];
         }
-        named_bar_sync(1, PW_CONSUMERS);
+        named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
 #pragma unroll
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
@@ -428,11 +431,16 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-
-        if constexpr (!M::ITEM1) {
-            double* r = red + (t & 1) * (PW_CONSUMER_WARPS * kMaxNodesPerPass);
+        if constexpr (M::ITEM1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        } else {
+            // Tile total per node: lanes -> warp (shuffles) -> per-warp slot in one of 4 rotating
+            // buffers.  Every warp ARRIVES on the tile's named barrier and moves on; only the owner
+            // warp(s) -- the ones holding threads tid < B -- WAIT on it, then fold the 7 slots.  The
+            // smem stage is released after the arrival, which bounds any warp's lead to 3 tiles, so a
+            // buffer is never rewritten before the owners have read it.
+            double* r = red + (t & (PW_RED_BUFS - 1)) * (PW_CONSUMER_WARPS * kMaxNodesPerPass);
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
                 double v = accS[n];
@@ -440,13 +448,20 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 for (unsigned m = 16; m >= NB; m >>= 1) v += shfl_xor_f64(v, m);
                 if (pl == 0) r[warp * kMaxNodesPerPass + nb + 32 * n] = v;
             }
-            named_bar_sync(1, PW_CONSUMERS);
+            const int bar = PW_BAR_TILE0 + (int) (t & (PW_RED_BUFS - 1));
+            const bool owner_warp = (unsigned) (warp * 32) < B;
+            if (owner_warp)
+                named_bar_sync(bar, PW_CONSUMERS);
+            else
+                named_bar_arrive(bar, PW_CONSUMERS);
             if ((unsigned) tid < B) {
                 double tot = 0.0;
 #pragma unroll
                 for (int w = 0; w < PW_CONSUMER_WARPS; ++w) tot += r[w * kMaxNodesPerPass + tid];
                 own.add_tile(tot, t1, a.item_rows, a.row_end);
             }
+            __syncwarp();  // owners have read the slots before this warp frees the stage
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
         ++t;
     }
@@ -466,7 +481,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 red[PW_CONSUMER_WARPS * kMaxNodesPerPass + warp * kMaxNodesPerPass + nb + 32 * n] = q;
             }
         }
-        named_bar_sync(1, PW_CONSUMERS);
+        named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
         if ((unsigned) tid < B) {
 #pragma unroll
             for (int w = 0; w < PW_CONSUMER_WARPS; ++w) {
@@ -480,12 +495,12 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         own.store(rec, tid);
         __threadfence();
     }
-    named_bar_sync(1, PW_CONSUMERS);
+    named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
     if (tid == 0) {
         const unsigned prev = atomicAdd(a.ticket, 1u);
         flag[0] = (prev == gridDim.x - 1);
     }
-    named_bar_sync(1, PW_CONSUMERS);
+    named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
     if (!flag[0]) return;
 
     // ---------------------------------------------------------------------- last CTA: finalize
@@ -493,7 +508,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     {
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
-                       B, red, 1, PW_CONSUMERS, S, Q);
+                       B, red, PW_BAR_ALL, PW_CONSUMERS, S, Q);
         if ((unsigned) tid < B) {
             a.out[tid] = S;
             a.out[B + tid] = Q;
