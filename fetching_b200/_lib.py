@@ -30,14 +30,46 @@ class ModelDesc(C.Structure):
     ]
 
 
-# every symbol include/pfetch.h declares: (restype, argtypes)
+class ChainConfig(C.Structure):
+    """struct pf_chain_config (include/pfetch.h)."""
+    _fields_ = [
+        ("frontier", C.c_uint32), ("scheduling_policy", C.c_uint32), ("chain_length", C.c_uint64),
+        ("correlation", C.c_double), ("reassign_ratio", C.c_double), ("dimension", C.c_uint32),
+        ("threshold", C.c_int32), ("verbose", C.c_int32), ("print_tsv", C.c_int32), ("seed", C.c_uint32),
+        ("deferred_proposals", C.c_uint32), ("tau", C.c_double), ("initial_theta", C.POINTER(C.c_double)),
+    ]
+
+
+class ChainStats(C.Structure):
+    """struct pf_chain_stats (include/pfetch.h)."""
+    _fields_ = [
+        ("levels", C.c_uint64), ("rows", C.c_uint64), ("engine_calls", C.c_uint64), ("nodes_scored", C.c_uint64),
+        ("max_frontier", C.c_uint64), ("allocated_nodes", C.c_uint64), ("recycled_nodes", C.c_uint64),
+        ("seconds", C.c_double), ("eval_seconds", C.c_double),
+    ]
+
+
 _dp = C.POINTER(C.c_double)
+ROW_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_int, C.c_double, _dp, C.c_uint32)
+JOB_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_char_p, C.c_uint64, C.c_uint64,
+                     C.c_uint64, C.c_double, _dp, C.c_uint32)
+EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, _dp, _dp, _dp)
+
+# every symbol include/pfetch.h declares: (restype, argtypes)
 SYMBOLS = {
     "pf_engine_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
     "pf_engine_destroy": (None, [C.c_void_p]),
     "pf_engine_data_size": (C.c_uint64, [C.c_void_p]),
     "pf_engine_theta_len": (C.c_uint32, [C.c_void_p]),
     "pf_engine_max_frontier": (C.c_uint32, [C.c_void_p]),
+    "pf_engine_model": (C.c_int, [C.c_void_p]),
+    "pf_engine_dim": (C.c_uint32, [C.c_void_p]),
+    "pf_engine_components": (C.c_uint32, [C.c_void_p]),
+    "pf_chain_run": (C.c_int, [C.c_void_p, C.POINTER(ChainConfig), ROW_FN, JOB_FN, C.c_void_p,
+                               C.POINTER(ChainStats)]),
+    "pf_chain_run_with_evaluator": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(ChainConfig),
+                                              EVAL_FN, C.c_void_p, ROW_FN, JOB_FN, C.c_void_p,
+                                              C.POINTER(ChainStats)]),
     "pf_eval_frontier": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp]),
     "pf_eval_frontier_range": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_uint64, C.c_uint64,
                                          C.POINTER(C.c_uint64), _dp, _dp]),

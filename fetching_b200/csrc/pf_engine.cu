@@ -374,6 +374,12 @@ uint32_t pf_engine_max_frontier(const pf_engine* e) {
     return e ? reinterpret_cast<const Engine*>(e)->max_frontier : 0;
 }
 
+int pf_engine_model(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->desc.model : 0; }
+
+uint32_t pf_engine_dim(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->dim : 0; }
+
+uint32_t pf_engine_components(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->K : 0; }
+
 uint64_t pf_engine_launch_count(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->launches : 0; }
 
 int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {

@@ -116,6 +116,9 @@ PF_API void pf_engine_destroy(pf_engine* e);
 PF_API uint64_t pf_engine_data_size(const pf_engine* e); /* items held by this engine */
 PF_API uint32_t pf_engine_theta_len(const pf_engine* e); /* doubles per node */
 PF_API uint32_t pf_engine_max_frontier(const pf_engine* e); /* nodes scored per kernel pass; larger B is chunked */
+PF_API int pf_engine_model(const pf_engine* e);           /* enum pf_model */
+PF_API uint32_t pf_engine_dim(const pf_engine* e);
+PF_API uint32_t pf_engine_components(const pf_engine* e);
 
 /* Score B frontier nodes over ALL items.  thetas: HOST [B][theta_len]; sum, sum_sq: HOST [B]
  * (overwritten).  Host->device copy of thetas, kernels, optional all-reduce, device->host copy
@@ -144,6 +147,62 @@ PF_API double pf_blasso_log_prior(const double* theta, uint32_t p, double tau);
  * pf_nccl_unique_id fills a 128-byte id on one rank; ship it to the others out of band. */
 PF_API int pf_nccl_unique_id(void* id128);
 PF_API int pf_engine_comm_init(pf_engine* e, const void* id128, int rank, int nranks);
+
+/* ---- a whole chain through the engine (host side: speculative tree + sampler + frontier hand-off) ----
+ *
+ * Equivalent of `mpirun -np frontier+1 ./fetching -S <sampler> -l chain_length -s policy -c correlation
+ * -d dimension -r reassign_ratio [-t] [-p]` (tree.cc:43-170): the master's speculative tree keeps
+ * drawing uniforms and proposals from the same replayable streams, but every scheduling burst
+ * (masterloop.cc:108-117) is scored by ONE pf_eval_frontier call instead of one MPI worker per node.
+ * The sampler follows the engine's model.  `row` receives every chain level the reference would
+ * print (stype.cc:67-84); `job` (optional) receives every JobInfo handed out and the proposal it
+ * produced, for tree-indexing parity tests. */
+typedef struct pf_chain_config {
+    uint32_t frontier;           /* virtual workers == nodes per engine call (mpirun -np minus 1) */
+    uint32_t scheduling_policy;  /* -s: 0 naive, 1 constant, 2 predictive (master.hh:29-33) */
+    uint64_t chain_length;       /* -l */
+    double correlation;          /* -c (0 -> 0.99) */
+    double reassign_ratio;       /* -r */
+    uint32_t dimension;          /* -d: initial proposal scale log(2.38^2 / d) (master.cc:25) */
+    int32_t threshold;           /* -t */
+    int32_t verbose;             /* -p: per-level table on stderr (master.cc:324-345) */
+    int32_t print_tsv;           /* print `time depth accept metric_sum theta` rows on stdout */
+    uint32_t seed;               /* mixture: seed of first_proposal (pymixture.py:71) */
+    uint32_t deferred_proposals; /* 0: the tree learns a proposal as soon as it is made (MasterTester-like);
+                                    1: only when the master reads SETPROPOSAL, so jobs carry replay paths */
+    double tau;                  /* lasso prior rate (0 -> 5.0, pyblasso.py:32) */
+    const double* initial_theta; /* lasso: optional initial (sigma, beta); NULL -> (1, 0, ..., 0) */
+} pf_chain_config;
+
+typedef struct pf_chain_stats {
+    uint64_t levels;        /* completed chain steps */
+    uint64_t rows;          /* rows delivered to `row` */
+    uint64_t engine_calls;  /* frontier batches == kernel passes */
+    uint64_t nodes_scored;  /* log-likelihood evaluations */
+    uint64_t max_frontier;
+    uint64_t allocated_nodes, recycled_nodes;
+    double seconds, eval_seconds;
+} pf_chain_stats;
+
+typedef void (*pf_chain_row_fn)(void* user, uint64_t depth, int accept, double metric_sum, const double* theta,
+                                uint32_t theta_len);
+typedef void (*pf_chain_job_fn)(void* user, uint64_t id, uint64_t generation, int state, const char* path,
+                                uint64_t random_position, uint64_t proposal_random_position,
+                                uint64_t next_random_position, double log_prior, const double* theta,
+                                uint32_t theta_len);
+
+PF_API int pf_chain_run(pf_engine* e, const pf_chain_config* cfg, pf_chain_row_fn row, pf_chain_job_fn job,
+                        void* user, pf_chain_stats* stats);
+
+/* The same host machinery (tree, sampler, frontier hand-off) with a caller-supplied frontier
+ * evaluator instead of the GPU engine: eval(user, B, thetas[B][theta_len], sum[B], sum_sq[B]) -> 0.
+ * Needs no device; it exists so the host logic can be exercised anywhere (the CPU test-suite
+ * plugs the oracle in here) and so another evaluator can sit behind the same tree. */
+typedef int (*pf_chain_eval_fn)(void* user, uint32_t B, const double* thetas, double* sum, double* sum_sq);
+PF_API int pf_chain_run_with_evaluator(int model, uint32_t dim, uint32_t components, uint64_t data_size,
+                                       const pf_chain_config* cfg, pf_chain_eval_fn eval, void* eval_user,
+                                       pf_chain_row_fn row, pf_chain_job_fn job, void* user,
+                                       pf_chain_stats* stats);
 
 /* Options. */
 enum pf_option {

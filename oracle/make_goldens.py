@@ -128,6 +128,37 @@ def gen_chains():
         print(name, len(out.splitlines()), "rows")
 
 
+FRONTIER_TRACES = {
+    # file: pf_ref arguments -- the REFERENCE JobTree/run_master/samplers driven by the product's
+    # FrontierCommunicator header (oracle/ref_driver.cc, `frontier`)
+    "frontier_trace_normal_W8.tsv": ["frontier", "normal", "-W", "8", "-d", "10000", "-l", "80"],
+    "frontier_trace_normal_W16_deferred_naive.tsv": ["frontier", "normal", "-W", "16", "-d", "10000", "-l", "60", "-s", "0",
+                                                     "--deferred"],
+    "frontier_trace_normal_W1.tsv": ["frontier", "normal", "-W", "1", "-d", "10000", "-l", "30"],
+    "frontier_trace_normal_W64_const.tsv": ["frontier", "normal", "-W", "64", "-d", "10000", "-l", "60", "-s", "1"],
+    "frontier_trace_boltzmann_W8.tsv": ["frontier", "boltzmann", "-W", "8", "-d", "10000", "-l", "80"],
+    "frontier_trace_boltzmann_W5_deferred.tsv": ["frontier", "boltzmann", "-W", "5", "-d", "10000", "-l", "60", "--deferred"],
+}
+
+
+def gen_frontier_traces():
+    for name, args in FRONTIER_TRACES.items():
+        out = subprocess.run([orc.REF_BIN, *args], check=True, capture_output=True, text=True).stdout
+        rows = [l for l in out.splitlines() if l.startswith("R")]
+        # the chain itself must be the one MasterTester produces (chain_*.tsv), whatever the frontier
+        gold = orc.parse_chain(open(os.path.join(GOLD, "chain_%s_d10000.tsv" % args[1])).read())
+        for r, g in zip(rows, gold):
+            f = r.split("\t")
+            assert (int(f[1]), int(f[2]), bytes.fromhex(f[4])) == (g[0], g[1], g[3]), (name, r)
+            assert abs(float(f[3]) - g[2]) <= 1e-12 * abs(g[2])
+        with open(os.path.join(GOLD, name), "w") as f:
+            f.write("# generated by oracle/make_goldens.py: pf_ref %s\n" % " ".join(args))
+            f.write("# J id generation state path random_position proposal_random_position next_random_position "
+                    "log_prior theta(hex)\n# R depth accept metric_sum theta(hex)\n")
+            f.write(out)
+        print(name, len(out.splitlines()), "lines")
+
+
 def gen_ref_normal():
     n = 10000
     data = orc.normal_dataset(n)
@@ -224,6 +255,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     subprocess.run(["make", "-s", "-C", HERE, "all"], check=True)
     gen_chains()
+    gen_frontier_traces()
     gen_ref_normal()
     gen_py_models()
     for f in sorted(os.listdir(GOLD)):

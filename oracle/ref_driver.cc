@@ -17,6 +17,10 @@
  *   normal-bench N B REPS        times evaluate_many for B nodes (CPU baseline, kind
  *                                "reference", one thread per node like one MPI worker per node)
  *   data N                       prints the first values of the normal.cc:41-46 dataset
+ *   frontier SAMPLER ...         the reference JobTree + run_master driven by the product's
+ *                                FrontierCommunicator (whole scheduling bursts scored at once by the
+ *                                reference's own evaluate_many): prints every JobInfo handed out
+ *                                (J rows) and every chain level (R rows) -- tests/golden/frontier_trace_*.tsv
  *
  * Output of `chain` is the golden-vector format of tests/golden/chain_*.tsv:
  *   depth <TAB> accept <TAB> metric_sum(%.17g) <TAB> theta(hex bytes) <TAB> unparse(theta)
@@ -28,6 +32,11 @@
 #include <chrono>
 #include <thread>
 #include <vector>
+
+// The PRODUCT's frontier communicator (header-only, generic over the tree / record types),
+// instantiated here with the REFERENCE's JobTree, records and samplers and a CPU evaluator: the
+// traces it prints are the goldens the product (its own tree + the GPU engine) must reproduce.
+#include "frontier_comm.hpp"
 
 namespace {
 
@@ -112,6 +121,97 @@ int cmd_chain(int argc, char** argv) {
         mt.run(*tree);
     }
     return 0;
+}
+
+// ---- reference tree under the product's frontier communicator ---------------------------------
+struct RefTypes {
+    using JobInfo = ::JobInfo;
+    using ProposalInfo = ::ProposalInfo;
+    using MetricChange = ::MetricChange;
+    using AbandonInfo = ::AbandonInfo;
+};
+static_assert(MSG_W2M_REGISTER == (int) pf::host::FC_REGISTER && MSG_W2M_WANTWORK == (int) pf::host::FC_WANTWORK &&
+                  MSG_W2M_SETPROPOSAL == (int) pf::host::FC_SETPROPOSAL && MSG_W2M_UPDATE == (int) pf::host::FC_UPDATE &&
+                  MSG_W2M_QUIT == (int) pf::host::FC_QUIT,
+              "message tags differ from the reference's (protocol.hh:32-41)");
+
+struct RefTrace {
+    void job(const JobInfo& in, const ProposalInfo& out) {
+        printf("J\t%zu\t%zu\t%d\t%s\t%zu\t%zu\t%zu\t%.17g\t%s\n", in.id, in.generation, in.state,
+               in.path.empty() ? "-" : in.path.c_str(), in.random_position, out.random_position,
+               out.next_random_position, out.log_prior, hex(out.proposal).c_str());
+    }
+};
+
+template <typename S>
+struct RefEvaluator {  // what MasterTester::check_update does per node (testmaster.cc:170-184), whole node at once
+    S sampler;
+    size_t n;
+    void operator()(const std::vector<pf::host::FrontierJob>& jobs, std::vector<double>& sum, std::vector<double>& sq) {
+        for (size_t i = 0; i != jobs.size(); ++i) {
+            JobNode* jn = tree->node(jobs[i].id);
+            JobInfo job;
+            job.state = JobInfo::s_has_proposal;
+            job.theta = jobs[i].theta;
+            job.random_position = jn ? jn->random_position() : 0;
+            (void) sampler.load(job);
+            sampler.prepare();
+            double s = 0, q = 0;
+            sampler.evaluate_many(0, n, s, q);
+            sum[i] = s;
+            sq[i] = q;
+        }
+    }
+};
+
+template <typename T>
+class TraceHook : public SamplerType {
+  public:
+    std::string unparse(const std::string& theta) const { return load_unparse_theta<T>(theta); }
+    void notify(const JobTree&, size_t depth, const double metric_sum, const std::string& theta, bool accept) {
+        printf("R\t%zu\t%d\t%.17g\t%s\n", depth, (int) accept, metric_sum, hex(theta).c_str());
+    }
+};
+
+template <typename S, typename T>
+int run_frontier(const S& sampler, size_t workers, size_t data_size, size_t levels, size_t policy, double reassign,
+                 bool eager) {
+    TraceHook<T> hook;
+    tree = new JobTree(workers + 1, levels, &hook, policy, 0.99, 1);
+    tree->set_reassign_ratio(reassign);
+    tree->set_require_comparison_theta(false);
+    tree->set_threshold(false);
+    RefEvaluator<S> evaluator{sampler, data_size};
+    RefTrace trace;
+    typedef pf::host::FrontierCommunicator<JobTree, S, RefTypes, RefEvaluator<S>, RefTrace> Comm;
+    Comm comm(*tree, sampler, evaluator, (int) workers, data_size, &trace, eager);
+    tree->run_master<Comm, typename Comm::Request, typename Comm::Status>(comm, JobTree::run_behavior().quiet(true));
+    printf("# levels %zu engine_calls %zu nodes_scored %zu max_batch %zu\n", tree->completed_depth(),
+           comm.stats().engine_calls, comm.stats().nodes_scored, comm.stats().max_batch);
+    return 0;
+}
+
+int cmd_frontier(int argc, char** argv) {
+    const char* sampler_name = "normal";
+    size_t workers = 8, data_size = 10000, levels = 50, policy = PREDICTIVE;
+    double reassign = 1.1;
+    bool eager = true;
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
+        if (a == "--deferred") eager = false;
+        else if (a == "-W") workers = strtoull(next(), 0, 0);
+        else if (a == "-d") data_size = strtoull(next(), 0, 0);
+        else if (a == "-l") levels = strtoull(next(), 0, 0);
+        else if (a == "-s") policy = strtoull(next(), 0, 0);
+        else if (a == "-r") reassign = strtod(next(), 0);
+        else sampler_name = argv[i];
+    }
+    if (strcmp(sampler_name, "boltzmann") == 0)
+        return run_frontier<BoltzmannSampler, double>(BoltzmannSampler(), workers, data_size, levels, policy, reassign, eager);
+    double* data = normal_dataset(data_size);
+    NormalSampler<2> sampler(data, data_size);
+    return run_frontier<NormalSampler<2>, NormalTheta<2> >(sampler, workers, data_size, levels, policy, reassign, eager);
 }
 
 struct EvalHeader {
@@ -224,7 +324,7 @@ int main(int argc, char** argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: pf_ref unit | chain [normal|boltzmann] [-n C] [-d N] [-b B] [-l L] [-s P] "
                         "[-D dim] [-r R] [-c C] [-t] | normal-eval IN OUT | boltz-eval IN OUT | "
-                        "normal-bench N NODES REPS [THREADS] | data N\n");
+                        "normal-bench N NODES REPS [THREADS] | data N | frontier [normal|boltzmann] [-W W] [-d N] [-l L] [-s P] [-r R]\n");
         return 1;
     }
     std::string cmd = argv[1];
@@ -243,6 +343,8 @@ int main(int argc, char** argv) {
     else if (cmd == "normal-bench" && argc >= 5)
         return cmd_normal_bench(strtoull(argv[2], 0, 0), strtoull(argv[3], 0, 0),
                                 strtoull(argv[4], 0, 0), argc > 5 ? strtoull(argv[5], 0, 0) : 0);
+    else if (cmd == "frontier")
+        return cmd_frontier(argc - 2, argv + 2);
     else if (cmd == "data" && argc == 3) {
         size_t n = strtoull(argv[2], 0, 0);
         double* d = normal_dataset(n);

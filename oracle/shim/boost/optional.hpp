@@ -7,6 +7,7 @@ template <typename T> class optional : public std::optional<T> {
   public:
     optional() {}
     optional(const T& v) : std::optional<T>(v) {}
+    optional(const std::optional<T>& o) : std::optional<T>(o) {}  /* lets a std::optional-returning Communicator drive run_master */
     T& get() { return **this; }
     const T& get() const { return **this; }
 };

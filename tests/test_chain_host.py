@@ -1,0 +1,119 @@
+"""Host logic on the CPU: the product's speculative tree (SpecTree), executors and frontier
+communicator against traces of the REFERENCE's own JobTree / run_master / samplers.
+
+The golden traces (tests/golden/frontier_trace_*.tsv) were produced by oracle/_ref/pf_ref, i.e.
+the reference's C++ compiled in place, driven by the same FrontierCommunicator header.  Here the
+product's tree + host executors are run with the ORACLE as frontier evaluator (through
+pf_chain_run_with_evaluator; no GPU involved) and must reproduce, bit for bit: every node id,
+generation, job state, replay path and random-stream position (tree indexing / node ordering),
+every proposal (theta bytes) and every accept/reject decision.  metric_sum: 1e-10 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TRACES = {
+    "frontier_trace_normal_W8.tsv": dict(model="normal", frontier=8, levels=80),
+    "frontier_trace_normal_W16_deferred_naive.tsv": dict(model="normal", frontier=16, levels=60, policy=0, deferred=True),
+    "frontier_trace_normal_W1.tsv": dict(model="normal", frontier=1, levels=30),
+    "frontier_trace_normal_W64_const.tsv": dict(model="normal", frontier=64, levels=60, policy=1),
+    "frontier_trace_boltzmann_W8.tsv": dict(model="boltzmann", frontier=8, levels=80),
+    "frontier_trace_boltzmann_W5_deferred.tsv": dict(model="boltzmann", frontier=5, levels=60, deferred=True),
+}
+
+
+def parse_trace(path):
+    jobs, rows = [], []
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "J":
+            jobs.append((int(f[1]), int(f[2]), int(f[3]), "" if f[4] == "-" else f[4], int(f[5]), int(f[6]), int(f[7]),
+                         float(f[8]), bytes.fromhex(f[9])))
+        elif f[0] == "R":
+            rows.append((int(f[1]), int(f[2]), float(f[3]), bytes.fromhex(f[4])))
+    return jobs, rows
+
+
+def check_against_trace(res, path):
+    jobs, rows = parse_trace(path)
+    got_jobs = [(j[0], j[1], j[2], j[3], j[4], j[5], j[6], j[7], j[8].tobytes()) for j in res.jobs]
+    assert len(got_jobs) == len(jobs)  # the very same nodes are handed out, in the same order
+    for a, b in zip(got_jobs, jobs):
+        assert a == b, (a[:8], b[:8])
+    assert len(res.depth) == len(rows)
+    for i, (depth, accept, metric_sum, theta) in enumerate(rows):
+        assert (res.depth[i], res.accept[i], res.theta[i].tobytes()) == (depth, accept, theta), i
+        assert abs(res.metric_sum[i] - metric_sum) <= 1e-10 * abs(metric_sum), i
+
+
+def oracle_run(orc, cfg, **extra):
+    from fetching_b200 import _lib, chain
+    if cfg["model"] == "normal":
+        data = orc.normal_dataset(10000)
+        ev = lambda th: orc.normal_frontier(data, th)
+        model, dim = _lib.MODEL_NORMAL, 2
+    else:
+        def ev(th):
+            out = np.array([orc.boltzmann_scalar_eval(float(t[0]), 10000) for t in th])
+            return out[:, 0], out[:, 1]
+        model, dim = _lib.MODEL_BOLTZMANN_SCALAR, 1
+    return chain.run_chain_with_evaluator(model, dim, 0, 10000, ev, chain_length=cfg["levels"], frontier=cfg["frontier"],
+                                          policy=cfg.get("policy", 2), deferred_proposals=cfg.get("deferred", False),
+                                          trace_jobs=True, **extra)
+
+
+@pytest.mark.parametrize("name", sorted(TRACES))
+def test_tree_indexing_and_chain_match_reference_trace(orc, name):
+    from fetching_b200 import build
+    build.build()
+    res = oracle_run(orc, TRACES[name])
+    check_against_trace(res, os.path.join(GOLD, name))
+    assert res.stats["max_frontier"] <= TRACES[name]["frontier"] and res.stats["engine_calls"] > 0
+
+
+@pytest.mark.parametrize("frontier", [1, 2, 3, 7, 33])
+def test_chain_does_not_depend_on_frontier_size(orc, frontier):
+    """The invariant the reference is built on: same chain whatever was speculated."""
+    res = oracle_run(orc, dict(model="normal", frontier=frontier, levels=120))
+    gold = orc.parse_chain(open(os.path.join(GOLD, "chain_normal_d10000.tsv")).read())
+    for i in range(121):
+        assert (res.depth[i], res.accept[i], res.theta[i].tobytes()) == (gold[i][0], gold[i][1], gold[i][3])
+        assert abs(res.metric_sum[i] - gold[i][2]) <= 1e-10 * abs(gold[i][2])
+    # SURVEY 8c.3 probe goldens
+    assert res.accept[:9].tolist() == [1, 1, 1, 1, 0, 1, 1, 0, 1]
+
+
+def test_boltzmann_chain_matches_mastertester_golden(orc):
+    res = oracle_run(orc, dict(model="boltzmann", frontier=9, levels=300))
+    gold = orc.parse_chain(open(os.path.join(GOLD, "chain_boltzmann_d10000.tsv")).read())
+    assert len(res.depth) == len(gold) == 301
+    for i, g in enumerate(gold):
+        assert (res.depth[i], res.accept[i], res.theta[i].tobytes()) == (g[0], g[1], g[3])
+        assert abs(res.metric_sum[i] - g[2]) <= 1e-12 * abs(g[2])
+
+
+def test_native_mixture_and_lasso_chains_run_and_are_frontier_invariant(orc):
+    """The native samplers behind the same tree: the chain must not depend on the frontier size."""
+    from fetching_b200 import _lib, chain, models
+    data, pos = models.mixture_dataset(4000, 8, 2, seed=3)
+    ev = lambda th: orc.mixture_frontier(data, th, 500)
+    runs = [chain.run_chain_with_evaluator(_lib.MODEL_MIXTURE, 2, 8, 8, ev, chain_length=40, frontier=f, dimension=16,
+                                           seed=0) for f in (1, 6)]
+    assert np.array_equal(runs[0].theta, runs[1].theta) and np.array_equal(runs[0].accept, runs[1].accept)
+    # first_proposal is numpy's: np.random.seed(0); 4 * np.random.random((8, 2)) - 2   (pymixture.py:69-73)
+    np.random.seed(0)
+    assert np.array_equal(runs[0].theta[0], (4.0 * np.random.random((8, 2)) - 2.0).ravel())
+    assert 0 < runs[0].accept[1:].sum() < 40
+
+    X, y, beta = models.blasso_dataset(3000, 6, seed=1)
+    ev = lambda th: orc.blasso_frontier(X, y, th, 500)
+    init = np.concatenate([[1.0], beta])
+    runs = [chain.run_chain_with_evaluator(_lib.MODEL_BLASSO, 6, 0, 6, ev, chain_length=30, frontier=f, dimension=7,
+                                           initial_theta=init, trace_jobs=True) for f in (1, 5)]
+    assert np.array_equal(runs[0].theta, runs[1].theta) and np.array_equal(runs[0].accept, runs[1].accept)
+    assert np.all(runs[0].theta[:, 0] > 0)  # sigma stays positive (pyblasso.py:117-121)
+    for j in runs[1].jobs:  # log_prior travels with the proposal (python.cc:168-176 -> pyblasso.py:123-133)
+        assert abs(j[7] - orc.blasso_log_prior(j[8])) <= 1e-12 * abs(j[7])
