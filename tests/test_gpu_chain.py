@@ -59,7 +59,9 @@ def test_gpu_normal_chain_c1_full_size(fb, orc):
         a = chain.run_chain(e, chain_length=100, frontier=8)
         b = chain.run_chain(e, chain_length=100, frontier=64)
     assert np.array_equal(a.theta, b.theta) and np.array_equal(a.accept, b.accept)
-    assert np.array_equal(a.metric_sum, b.metric_sum)  # fixed-order reductions: B does not change a node's sum
+    # a node's sum is bit-stable for a given launch geometry; the lane mapping (hence the summation
+    # order) follows the frontier size, so across B it agrees to rounding only
+    assert np.max(np.abs(a.metric_sum - b.metric_sum) / np.abs(a.metric_sum)) < 1e-12
     for i in (0, 1, 50, 100):
         s, _ = orc.normal_eval(data, a.theta[i])
         assert abs(a.metric_sum[i] - s) <= 1e-10 * abs(s)
