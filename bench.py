@@ -52,6 +52,15 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload, dtype, B):
+    """DRAM bytes per launch of the dominant kernel from an ncu --set full capture, if one was taken for
+    this exact configuration (profiles/traffic.json, written from profiles/*_full.md); else None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("%s/%s/%d" % (workload, dtype, B))
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -136,6 +145,25 @@ def algorithmic_bytes(kind, prm, rows_local, B, dtype):
     if kind == "boltzmann":
         return prm["D"] * prm["D"] * T + B * prm["D"] * 8 + 8 * B
     raise ValueError(kind)
+
+
+def fp64_view(kind, prm, rows_local, B, dtype, kern_ms, device):
+    """The mixture kernel is bound by the FP64 pipe, not by HBM: report how busy
+    that pipe is.  Numerator: FP64 instructions the kernel issues per (row, node) -- 129 for K=8, d=2,
+    counted in the SASS of the inner loop -- x rows x B; denominator: the FP64 FMA issue
+    rate measured on this GPU by pf_debug_fp64_probe (MEASURED_PEAKS.json has no FP64 figure)."""
+    if kind != "mixture" or dtype != "f64" or (prm["K"], prm["d"]) != (8, 2):
+        return None
+    import ctypes as C
+    from fetching_b200 import _lib
+    out = np.zeros(16)
+    _lib.check(_lib.load().pf_debug_fp64_probe(device, out.ctypes.data_as(C.POINTER(C.c_double))), "fp64 probe")
+    peak_tfma = float(out.max())
+    instr = 129.0 * rows_local * B
+    achieved = instr / (kern_ms * 1e-3) / 1e12
+    return {"bound": "fp64", "achieved": achieved, "peak": peak_tfma, "unit": "T FP64 instr-lanes/s (1 FMA = 1)",
+            "frac": achieved / peak_tfma, "peak_tflops": 2 * peak_tfma,
+            "note": "peak measured by pf_debug_fp64_probe; 129 FP64 instr per (row,node) from the inner-loop SASS"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -246,6 +274,7 @@ def main():
     ap.add_argument("--frontier", type=int, default=8, help="frontier nodes per step (B)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only)")
+    ap.add_argument("--chain-length", type=int, default=50, help="levels of the chain-steps/s measurement")
     args = ap.parse_args()
 
     desc, kind, prm = WORKLOADS[args.workload]
@@ -353,10 +382,27 @@ def main():
     t_e2e = float(te.item())
     assert np.allclose(s_host, result_dev[0], rtol=1e-12, atol=0), "host and device paths disagree"
 
-    # ---- dominant kernel alone (no all-reduce): roofline numerator, CUDA events on the launch stream
+    # ---- dominant kernel: the step is that one launch (+ a <= 1 KB all-reduce when sharded), so the
+    # CUDA-event time per step is its launch duration (an upper bound for N > 1)
     kern_ms = ms_total / K
-    if world > 1:
-        pass  # the step's only other work is a <= 1 KB all-reduce; report the step time as an upper bound
+
+    # ---- chain level: the speculative tree + sampler on the host, every scheduling burst scored by one
+    # engine call (pf_chain_run).  All ranks run the same deterministic chain in lock-step.
+    from fetching_b200 import chain as pf_chain
+    chain_kw = dict(chain_length=args.chain_length, frontier=B)
+    if kind == "mixture":
+        chain_kw.update(dimension=prm["K"] * prm["d"])
+    elif kind == "blasso":
+        chain_kw.update(dimension=prm["p"] + 1, initial_theta=np.concatenate([[1.0], shard["beta"]]))
+    elif kind == "boltzmann":
+        chain_kw.update(dimension=prm["D"])
+    barrier()
+    cres = pf_chain.run_chain(eng, **chain_kw)
+    torch.cuda.synchronize()
+    chain_info = {"steps_per_sec": cres.chain_steps_per_sec, "levels": int(cres.stats["levels"]),
+                  "engine_calls": int(cres.stats["engine_calls"]), "nodes_scored": int(cres.stats["nodes_scored"]),
+                  "frontier": B, "accept_rate": float(cres.accept[1:].mean()) if len(cres.accept) > 1 else None,
+                  "seconds": cres.stats["seconds"], "eval_seconds": cres.stats["eval_seconds"]}
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -373,10 +419,16 @@ def main():
                     "d2h_bytes_per_step": int(2 * B * 8), "ms_per_step": t_e2e / K * 1e3},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                         "frac": achieved / pk["hbm_gbs"],
+                         "traffic": measured_traffic(args.workload, args.dtype, B) if world == 1 else None,
+                         "peak_source": pk_src,
                          "kernel": "pw_frontier_kernel / mv_frontier_kernel (per-GPU shard, %d rows)" % rows_local,
                          "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kern_ms},
         }
+        line["chain"] = chain_info
+        fp64 = fp64_view(kind, prm, rows_local, B, args.dtype, kern_ms, local_rank)
+        if fp64:
+            line["roofline"]["fp64_pipe"] = fp64
         if world == 1:
             base, _, _ = cpu_leg(kind, prm, B, 3, 1)
             line["cpu_baseline"] = base
