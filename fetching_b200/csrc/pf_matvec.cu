@@ -37,7 +37,7 @@ constexpr int MV_MAX_TILE_ROWS = 256;
 constexpr int MV_NODES_PER_LANE = 8;
 constexpr int MV_XSTAGE_BYTES = MV_MAX_TILE_ROWS * MV_CHUNK_BYTES;                  // 32 KB
 constexpr int MV_BSTAGE_BYTES = MV_CHUNK_BYTES * kMaxNodesPerPass;                  // [chunk k][64 nodes] = 8 KB
-constexpr int MV_RED_DOUBLES = 2 * MV_CONSUMER_WARPS * kMaxNodesPerPass;
+constexpr int MV_RED_DOUBLES = 2 * 2 * MV_CONSUMER_WARPS * kMaxNodesPerPass;  // 2 buffers x (part A | part B) x warps x nodes
 
 constexpr size_t kMvSmem = 1024 /* alignment slack */ + (size_t) MV_STAGES * (MV_XSTAGE_BYTES + MV_BSTAGE_BYTES) +
                            MV_RED_DOUBLES * sizeof(double) + 2 * MV_STAGES * sizeof(uint64_t) + 16;
@@ -82,9 +82,11 @@ struct UnitIter {
             t0 = cur;
             unsigned long long e = cur + tile_rows;
             if (e > end_all) e = end_all;
-            unsigned long long ie = (cur / item_rows + 1) * item_rows;
-            if (ie > row_end) ie = row_end;
-            if (e > ie) e = ie;
+            if (item_rows < tile_rows) {  // small items: a tile never straddles one
+                unsigned long long ie = (cur / item_rows + 1) * item_rows;
+                if (ie > row_end) ie = row_end;
+                if (e > ie) e = ie;
+            }
             t1 = e;
             cur = e;
             c0 = 0;
@@ -100,8 +102,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     constexpr int KPV = 16 / (int) sizeof(T);             // k values per 16-byte vector
     constexpr int KCH = MV_CHUNK_BYTES / (int) sizeof(T);  // k values per chunk
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (the 128-byte swizzle pattern repeats every 8 rows = 1024 B).  The pad is ADDED
+    // to the array so the compiler still knows these are shared-memory addresses (LDS, not generic LD).
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* xstage = smem;
     unsigned char* bstage = smem + MV_STAGES * MV_XSTAGE_BYTES;
     double* red = reinterpret_cast<double*>(bstage + MV_STAGES * MV_BSTAGE_BYTES);
@@ -222,10 +226,17 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
-        // ---- epilogue for this unit, in registers
-        double part[MV_NODES_PER_LANE];
+        // ---- epilogue for this unit, in registers.  A lasso tile may contain ONE item boundary `ts`
+        // (items are at least a tile tall in that mode): rows before it go to partA, rows after to partB.
+        unsigned long long ts = t1;
+        if constexpr (!BOLTZ) {
+            const unsigned long long ie = (t0 / a.item_rows + 1) * a.item_rows;
+            if (ie < t1) ts = ie;
+        }
+        const bool split = ts < t1;
+        double partA[MV_NODES_PER_LANE], partB[MV_NODES_PER_LANE];
 #pragma unroll
-        for (int n = 0; n < MV_NODES_PER_LANE; ++n) part[n] = 0.0;
+        for (int n = 0; n < MV_NODES_PER_LANE; ++n) partA[n] = partB[n] = 0.0;
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
             const unsigned long long r = t0 + row_in_tile + 32 * i;
@@ -236,34 +247,52 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
                         unsigned node = g * MV_NODES_PER_LANE + n;
                         if (node >= B) node = B - 1;
                         const double xi = __ldg(&a.theta[(size_t) node * a.theta_len + r]);
-                        part[n] = fma(xi, (double) acc[i][n], part[n]);
+                        partA[n] = fma(xi, (double) acc[i][n], partA[n]);
                     }
                 } else {
                     const double yv = __ldg(&a.y[r]);
+                    const bool first = r < ts;
 #pragma unroll
                     for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
                         const double res = (double) acc[i][n] - yv;
-                        part[n] += cst[n] - res * res * hinv[n];
+                        const double lp = cst[n] - res * res * hinv[n];
+                        partA[n] += first ? lp : 0.0;
+                        partB[n] += first ? 0.0 : lp;
                     }
                 }
             }
         }
-        double* rbuf = red + (unit & 1) * (MV_CONSUMER_WARPS * kMaxNodesPerPass);
+        double* rbuf = red + (unit & 1) * (2 * MV_CONSUMER_WARPS * kMaxNodesPerPass);
 #pragma unroll
         for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
-            double v = part[n];
+            double v = partA[n];
             for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
             if (lane == 0) rbuf[rw * kMaxNodesPerPass + g * MV_NODES_PER_LANE + n] = v;
         }
+        if (split) {
+#pragma unroll
+            for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+                double v = partB[n];
+                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
+                if (lane == 0)
+                    rbuf[(MV_CONSUMER_WARPS + rw) * kMaxNodesPerPass + g * MV_NODES_PER_LANE + n] = v;
+            }
+        }
         named_bar_sync(1, MV_CONSUMERS);
         if ((unsigned) tid < B) {
-            double tot = 0.0;
             const unsigned RW = MV_CONSUMER_WARPS / NG;
+            double tot = 0.0;
             for (unsigned w = 0; w < RW; ++w) tot += rbuf[w * kMaxNodesPerPass + tid];
             if constexpr (BOLTZ)
                 own.S += tot;
-            else
-                own.add_tile(tot, t1, a.item_rows, a.row_end);
+            else {
+                own.add_tile(tot, ts, a.item_rows, a.row_end);
+                if (split) {
+                    double totB = 0.0;
+                    for (unsigned w = 0; w < RW; ++w) totB += rbuf[(MV_CONSUMER_WARPS + w) * kMaxNodesPerPass + tid];
+                    own.add_tile(totB, t1, a.item_rows, a.row_end);
+                }
+            }
         }
         ++unit;
     }
