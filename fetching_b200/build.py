@@ -77,13 +77,20 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
     host_cpp = sorted(os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))
-                      if f.endswith(".cpp")) if os.path.isdir(os.path.join(CSRC, "host")) else []
+                      if f.endswith(".cpp") and not f.endswith("_main.cpp"))
     link = [nvcc, *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17",
             "-Xcompiler", "-fPIC,-O2", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
             "-o", out, *objs, *host_cpp, "-lcuda", "-ldl"]
     if verbose:
         print(" ".join(link), flush=True)
     subprocess.run(link, check=True, env=env)
+    if out == LIB:  # the command-line front end (tree.cc equivalent), linked against the library next to it
+        cli = [ccbin[1] if ccbin else "g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+               os.path.join(CSRC, "host", "pfetch_main.cpp"), "-o", os.path.join(LIBDIR, "pfetch"),
+               "-L" + LIBDIR, "-lpfetch", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cli), flush=True)
+        subprocess.run(cli, check=True, env=env)
     return out
 
 

@@ -137,6 +137,7 @@ static void destroy(Engine* e) {
     cudaFree(e->d_out);
     cudaFree(e->d_part);
     cudaFree(e->d_betaT);
+    cudaFree(e->d_order);
     cudaFree(e->d_ticket);
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
@@ -312,6 +313,7 @@ static int create(const pf_model_desc* d, Engine** out) {
     PF_CUDA_F(cudaMalloc(&e->d_theta, tbytes));
     PF_CUDA_F(cudaMalloc(&e->d_out, 2 * kMaxNodesPerPass * 8));
     PF_CUDA_F(cudaMalloc(&e->d_part, (size_t) kMaxGrid * kPartSlots * kMaxNodesPerPass * 8));
+    PF_CUDA_F(cudaMalloc(&e->d_order, (size_t) kMaxNodesPerPass * 2 * sizeof(unsigned long long)));
     PF_CUDA_F(cudaMalloc(&e->d_ticket, 64));
     PF_CUDA_F(cudaMemsetAsync(e->d_ticket, 0, 64, e->stream));
     PF_CUDA_F(cudaMallocHost(&e->h_theta, tbytes));
@@ -323,7 +325,7 @@ static int create(const pf_model_desc* d, Engine** out) {
 }
 
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
-                     double* sum, double* sum_sq) {
+                     const uint64_t* order, double* sum, double* sum_sq) {
     PF_CUDA(cudaSetDevice(e.device));
     for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
         const uint32_t nb = B - b0 < e.max_frontier ? B - b0 : e.max_frontier;
@@ -332,7 +334,16 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         const size_t tbytes = (size_t) nb * e.theta_len * 8;
         memcpy(e.h_theta, th, tbytes);
         PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
-        int r = launch_model(e, nb, e.d_theta, e.d_out, first_item, n_items, e.stream);
+        int r;
+        if (order) {  // the reference's per-node visiting order (normal target; checked by the caller)
+            PF_CUDA(cudaMemcpyAsync(e.d_order, order + (size_t) 2 * b0, (size_t) nb * 2 * sizeof(uint64_t),
+                                    cudaMemcpyHostToDevice, e.stream));
+            const int k = launch_normal_ordered(e, nb, e.d_theta, e.d_out, e.d_order, first_item, n_items, e.stream);
+            if (k < 0) return PF_ERR_CUDA;
+            e.launches += (uint64_t) k;
+            r = PF_OK;
+        } else
+            r = launch_model(e, nb, e.d_theta, e.d_out, first_item, n_items, e.stream);
         if (r != PF_OK) return r;
         r = allreduce_out(e, e.d_out, nb, e.stream);
         if (r != PF_OK) return r;
@@ -398,7 +409,7 @@ int pf_eval_frontier(pf_engine* pe, uint32_t B, const double* thetas, double* su
         return PF_ERR_INVALID;
     }
     Engine& e = *reinterpret_cast<Engine*>(pe);
-    return pf::eval_host(e, B, thetas, 0, e.n_items, sum, sum_sq);
+    return pf::eval_host(e, B, thetas, 0, e.n_items, nullptr, sum, sum_sq);
 }
 
 int pf_eval_frontier_range(pf_engine* pe, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
@@ -414,14 +425,27 @@ int pf_eval_frontier_range(pf_engine* pe, uint32_t B, const double* thetas, uint
         return PF_ERR_SHAPE;
     }
     if (order) {
-        pf::set_error("StrideIndex-ordered partial ranges are not built yet");
-        return PF_ERR_UNSUPPORTED;
+        if (e.desc.model != PF_MODEL_NORMAL) {
+            pf::set_error("a visiting order only exists for the normal target (normalsampler.hh:115-119)");
+            return PF_ERR_UNSUPPORTED;
+        }
+        if (e.nranks > 1) {
+            pf::set_error("ordered ranges address the whole data set: not available on a row shard");
+            return PF_ERR_UNSUPPORTED;
+        }
+        for (uint32_t b = 0; b < B; ++b)
+            if (order[2 * b] == 0 || order[2 * b] >= e.n_rows || order[2 * b + 1] >= e.n_rows) {
+                if (!(e.n_rows == 1 && order[2 * b] == 1)) {
+                    pf::set_error("order[%u]: stride/start outside [0, n)", b);
+                    return PF_ERR_SHAPE;
+                }
+            }
     }
     if (e.desc.model == PF_MODEL_BOLTZMANN_DENSE && n_items != 1) {
         for (uint32_t b = 0; b < B; ++b) sum[b] = sum_sq[b] = 0.0;
         return PF_OK;
     }
-    return pf::eval_host(e, B, thetas, first_item, n_items, sum, sum_sq);
+    return pf::eval_host(e, B, thetas, first_item, n_items, order, sum, sum_sq);
 }
 
 int pf_eval_frontier_device(pf_engine* pe, uint32_t B, const double* d_thetas, double* d_out, void* cuda_stream) {

@@ -65,6 +65,7 @@ struct Engine {
     double* d_out = nullptr;     // [2][max_frontier]
     double* d_part = nullptr;    // [kMaxGrid][kPartSlots][64]
     void* d_betaT = nullptr;     // matvec coefficient panel
+    unsigned long long* d_order = nullptr;  // [max_frontier][2] StrideIndex (stride, start) per node
     unsigned int* d_ticket = nullptr;
     double* h_theta = nullptr;   // pinned staging
     double* h_out = nullptr;     // pinned staging
@@ -83,6 +84,8 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
                      uint64_t n_items, cudaStream_t s);
 int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
                   uint64_t n_items, cudaStream_t s);
+int launch_normal_ordered(Engine& e, uint32_t B, const double* d_theta, double* d_out,
+                          const unsigned long long* d_order, uint64_t first_item, uint64_t n_items, cudaStream_t s);
 int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,
                             cudaStream_t s);
 uint32_t pointwise_max_frontier(const Engine& e);

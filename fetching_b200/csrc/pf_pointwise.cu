@@ -420,7 +420,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         mbar_wait(&full[s], (t / PW_STAGES) & 1);
         const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB) & 15ull);
         const unsigned nrows = (unsigned) (t1 - t0);
-#pragma unroll(M::ITEM1 ? 2 : 1)
+#pragma unroll(M::ITEM1 ? 2 : 1)  // (2 rows in flight did not help the mixture: measured 9.5 vs 9.3 ms)
         for (unsigned j = slot; j < nrows; j += nslots) {
             CT x[DIM];
             load_row<T, DIM, CT>(base + (size_t) j * RB, x);
@@ -515,6 +515,72 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         }
     }
     if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Partial sums in the reference's per-node visiting order (normal target only): item i of node b
+// is data row (start_b + i * stride_b) mod n  (strideindex.hh:46-48; drawn in prepare(),
+// normalsampler.hh:115-119).  Every node walks its own permutation, so this is a gather: one
+// CTA column per node (blockIdx.y), rows fetched straight from global/L2 -- used for the partial
+// updates that feed the predictive scheduler (worker.hh:141-162), never for whole-data scoring.
+// Deterministic: per-CTA partials, summed in CTA order by ordered_finalize_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int D, typename T, bool GENERAL>
+__global__ void __launch_bounds__(256) normal_ordered_kernel(const T* __restrict__ data, unsigned long long n,
+                                                             const double* __restrict__ theta, unsigned theta_len,
+                                                             const unsigned long long* __restrict__ order,
+                                                             unsigned long long first, unsigned long long count,
+                                                             double* __restrict__ part) {
+    using M = NormalModel<D, T, GENERAL>;
+    using CT = typename M::CT;
+    __shared__ double red[2][8];
+    const unsigned b = blockIdx.y;
+    typename M::Node nd;
+    M::load(nd, theta + (size_t) b * theta_len, 0);
+    const unsigned long long stride = order[2 * b], start = order[2 * b + 1];
+    double S = 0.0, Q = 0.0;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned long long row = (start + (first + i) * stride) % n;
+        CT x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = (CT) __ldg(&data[row * D + j]);
+        const double v = (double) M::rowlp(nd, x);
+        S += v;
+        Q = fma(v, v, Q);
+    }
+    for (int m = 16; m >= 1; m >>= 1) {
+        S += shfl_xor_f64(S, m);
+        Q += shfl_xor_f64(Q, m);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[0][warp] = S;
+        red[1][warp] = Q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, q = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            s += red[0][w];
+            q += red[1][w];
+        }
+        part[((size_t) b * gridDim.x + blockIdx.x) * 2] = s;
+        part[((size_t) b * gridDim.x + blockIdx.x) * 2 + 1] = q;
+    }
+}
+
+__global__ void ordered_finalize_kernel(const double* part, unsigned nblocks, unsigned B, double* out) {
+    const unsigned b = threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0, q = 0.0;
+    for (unsigned c = 0; c < nblocks; ++c) {
+        s += part[((size_t) b * nblocks + c) * 2];
+        q += part[((size_t) b * nblocks + c) * 2 + 1];
+    }
+    out[b] = s;
+    out[B + b] = q;
 }
 
 // scalar Boltzmann (boltzmannsampler.hh:71-82): x = -theta/T; sum = x*count; sum_sq = x*x*count
@@ -686,6 +752,55 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
         return e.f32 ? dispatch_normal<float>(e, a, s, general) : dispatch_normal<double>(e, a, s, general);
     }
     return e.f32 ? dispatch_mixture<float>(e, a, s) : dispatch_mixture<double>(e, a, s);
+}
+
+
+namespace {
+template <int D, typename T>
+int launch_ordered_t(Engine& e, uint32_t B, const double* d_theta, double* d_out, const unsigned long long* d_order,
+                     uint64_t first, uint64_t count, bool general, cudaStream_t s) {
+    unsigned nblocks = (unsigned) ((count + 2047) / 2048);
+    if (nblocks > 128) nblocks = 128;
+    if (nblocks < 1) nblocks = 1;
+    const dim3 grid(nblocks, B);
+    if (general)
+        normal_ordered_kernel<D, T, true><<<grid, 256, 0, s>>>(static_cast<const T*>(e.d_data), e.n_rows, d_theta,
+                                                             e.theta_len, d_order, first, count, e.d_part);
+    else
+        normal_ordered_kernel<D, T, false><<<grid, 256, 0, s>>>(static_cast<const T*>(e.d_data), e.n_rows, d_theta,
+                                                              e.theta_len, d_order, first, count, e.d_part);
+    ordered_finalize_kernel<<<1, kMaxNodesPerPass, 0, s>>>(e.d_part, nblocks, B, d_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("ordered range kernels: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 2;
+}
+}  // namespace
+
+// d_order: device [B][2] = (stride, start) per node
+int launch_normal_ordered(Engine& e, uint32_t B, const double* d_theta, double* d_out,
+                          const unsigned long long* d_order, uint64_t first_item, uint64_t n_items, cudaStream_t s) {
+    if (n_items == 0) {
+        cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
+        return 0;
+    }
+    const bool general = e.normal_general;
+#define PF_ORD_CASE(Dv)                                                                                          \
+    case Dv:                                                                                                     \
+        return e.f32 ? launch_ordered_t<Dv, float>(e, B, d_theta, d_out, d_order, first_item, n_items, general, s) \
+                     : launch_ordered_t<Dv, double>(e, B, d_theta, d_out, d_order, first_item, n_items, general, s);
+    switch (e.dim) {
+        PF_ORD_CASE(1)
+        PF_ORD_CASE(2)
+        PF_ORD_CASE(3)
+        PF_ORD_CASE(4)
+        PF_ORD_CASE(8)
+    }
+#undef PF_ORD_CASE
+    set_error("normal target: dimension %u not built", e.dim);
+    return -1;
 }
 
 int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,

@@ -109,3 +109,24 @@ def test_gpu_dense_boltzmann_chain(fb, orc):
     assert np.array_equal(a.theta, b.theta) and np.array_equal(a.accept, b.accept)
     want = orc.boltzmann_dense_logp(W, a.theta[10])
     assert abs(a.metric_sum[10] - want) <= 1e-9 * max(1.0, abs(want))
+
+
+def test_cli_prints_the_reference_chain(orc):
+    """`pfetch -n 9 -l 60 normal ndata=10000` (tree.cc flags) prints the TSV of stype.cc:67-84; its depth /
+    accept / metric_sum(%.5f) / theta columns must equal what the reference prints for the same chain."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "fetching_b200", "lib", "pfetch")
+    p = subprocess.run([exe, "-n", "9", "-l", "60", "-p", "normal", "ndata=10000"], capture_output=True, text=True,
+                       timeout=120)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.strip().split("\n")
+    assert lines[0] == "time\tdepth\taccept\tmetric_sum\ttheta"
+    gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLD, "chain_normal_d10000.tsv")) if l[0] != "#"]
+    assert len(lines) - 1 == 61
+    for line, g in zip(lines[1:], gold):
+        f = line.split("\t")
+        assert f[1] == g[0] and f[2] == g[1] and f[4] == g[4], (line, g)
+        assert abs(float(f[3]) - float(g[2])) <= 1e-10 * abs(float(g[2])) + 1e-5  # printed with 5 decimals
+    assert "OK sample/s =" in p.stderr and "#depth last_executor allocated_nodes" in p.stderr
+    assert p.stderr.startswith("# 0 = ")

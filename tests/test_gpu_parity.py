@@ -114,6 +114,36 @@ def test_normal_item_ranges_add_up(fb, orc):
         assert rel(s1[b], w[0]) < TOL64 and rel(q1[b], w[1]) < TOL64
 
 
+def test_normal_ordered_partial_ranges(fb, orc):
+    """a3/a9: partial sums in the reference's per-node StrideIndex order (strideindex.hh:46-48), the
+    updates a worker sends every batch_size items (worker.hh:141-162)."""
+    from fetching_b200 import models
+    n = 10000
+    data = orc.normal_dataset(n)
+    th = models.normal_thetas(5, seed=4, center=(200, 100), scale=1.0)
+    th[4, 2:] = [2.0, 0.3, 1.5]  # one general covariance
+    order = np.array([orc.normal_prepare_draws(n, 2 * b)[:2] for b in range(5)], dtype=np.uint64)
+    with fb.FrontierEngine.normal(data) as e:
+        run_s, run_q = np.zeros(5), np.zeros(5)
+        for first in range(0, n, 1000):  # ten cumulative updates, like -b 1000
+            s, q = e.eval_frontier_range(th, first, 1000, order=order)
+            for b in range(5):
+                w = orc.normal_eval(data, th[b], int(order[b, 0]), int(order[b, 1]), first, 1000)
+                assert rel(s[b], w[0]) < TOL64 and rel(q[b], w[1]) < TOL64
+            run_s += s
+            run_q += q
+        full_s, full_q = e.eval_frontier(th)
+        assert rel(run_s, full_s) < 1e-12 and rel(run_q, full_q) < 1e-12  # a permutation: same totals
+        with pytest.raises(fb.PfetchError, match="PF_ERR_SHAPE"):
+            e.eval_frontier_range(th, 0, 10, order=np.array([[0, 0]] * 5, dtype=np.uint64))
+    # the golden values of the reference binary are sums in exactly this order
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_normal_eval.npz"))
+    st, off, _ = orc.normal_prepare_draws(n, 0)
+    with fb.FrontierEngine.normal(data) as e:
+        s, q = e.eval_frontier_range(g["thetas"], 0, n, order=np.array([[st, off]] * len(g["thetas"]), dtype=np.uint64))
+    assert rel(s, g["sum"]) < TOL64 and rel(q, g["sum_sq"]) < TOL64
+
+
 # ------------------------------------------------------------------------------------ mixture
 def test_mixture_vs_reference_python_golden(fb, py_models):
     """Golden values are outputs of the reference's own Mixture.evaluate (K = 8, d = 8)."""
