@@ -179,11 +179,13 @@ struct MixtureModel {
     using CT = typename ComputeOf<T>::type;
     struct Node {
         const CT* th;
-        const double* tab;  // 2^(j/32) in shared memory
+        const double* tab;    // 2^(j/256) in shared memory
+        const double2* ltab;  // {1/c_j, log c_j} in shared memory
     };
-    static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab) {
+    static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab, const double2* ltab) {
         nd.th = th_smem;
         nd.tab = tab;
+        nd.ltab = ltab;
     }
     // library exp/log: subnormal terms, log(0) = -inf, nan propagation exactly like numpy's
     static __device__ __noinline__ CT slow(const CT* th, const CT (&x)[D]) {
@@ -225,7 +227,7 @@ struct MixtureModel {
             lp += v[0];
         }
         if (needs_slow_path(lp)) return slow(nd.th, x);  // every component ~40 sigma away, or non-finite input
-        return log_pos_fast(lp);
+        return log_pos_fast(lp, nd.ltab);
     }
 };
 
@@ -240,11 +242,13 @@ struct MixtureModelRT {
     struct Node {
         const CT* th;
         const double* tab;
+        const double2* ltab;
         unsigned K;
     };
-    static __device__ void load(Node& nd, const CT* th_smem, unsigned K, const double* tab) {
+    static __device__ void load(Node& nd, const CT* th_smem, unsigned K, const double* tab, const double2* ltab) {
         nd.th = th_smem;
         nd.tab = tab;
+        nd.ltab = ltab;
         nd.K = K;
     }
     static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
@@ -270,7 +274,7 @@ struct MixtureModelRT {
             }
             return (CT) log(l2);
         }
-        return log_pos_fast(lp);
+        return log_pos_fast(lp, nd.ltab);
     }
 };
 
@@ -382,7 +386,9 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     typename M::Node nd[NPL];
     if constexpr (M::THETA_IN_SMEM) {
         __shared__ __align__(16) double exp2_tab[kExp2TabSize];
+        __shared__ __align__(16) double2 log_tab[256];
         for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
+        for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
         for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
@@ -393,7 +399,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
             if (node >= B) node = B - 1;  // idle lanes shadow the last node; their sums are dropped
-            M::load(nd[n], th_smem + node * stride, a.K, exp2_tab);
+            M::load(nd[n], th_smem + node * stride, a.K, exp2_tab, log_tab);
         }
     } else {
 #pragma unroll
@@ -597,7 +603,9 @@ __global__ void boltzmann_scalar_kernel(const double* theta, double* out, unsign
 __global__ void debug_math_kernel(int which, const double* in, double* out, size_t n) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     __shared__ double tab[kExp2TabSize];
+    __shared__ __align__(16) double2 ltab[256];
     for (int i = threadIdx.x; i < kExp2TabSize; i += blockDim.x) tab[i] = kExp2Tab[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) ltab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
     __syncthreads();
     if (i >= n) return;
     const double x = in[i];
@@ -606,6 +614,7 @@ __global__ void debug_math_kernel(int which, const double* in, double* out, size
         case 0: r = exp_neg_half(x, tab); break;
         case 1: r = log_pos(x); break;
         case 2: r = (double) exp_neg_half((float) x, tab); break;
+        case 4: r = log_pos_tab(x, ltab); break;
         default: r = (double) log_pos((float) x); break;
     }
     out[i] = r;

@@ -225,6 +225,8 @@ PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int
  * independent chains per thread in {1,2,4,8}; out16[4*w + i].  The largest entry is the FP64
  * roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
 PF_API int pf_debug_fp64_probe(int device, double* out16);
+/* Diagnostics: DFMA rate (1e12/s) with k = 0..3 integer multiply-adds interleaved per DFMA (issue-slot model). */
+PF_API int pf_debug_issue_probe(int device, double* out4);
 
 #ifdef __cplusplus
 }

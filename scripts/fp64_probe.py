@@ -8,3 +8,7 @@ print("TFMA/s (x2 = TFLOP/s); rows: warps/SM 4,8,16,32; cols: ILP 1,2,4,8")
 print(np.round(out.reshape(4, 4), 3))
 clk = 1.965e9; sms = 148
 print("FMA/clk/SM:"); print(np.round(out.reshape(4,4) * 1e12 / clk / sms, 2))
+
+out4 = np.zeros(4)
+_lib.check(lib.pf_debug_issue_probe(0, out4.ctypes.data_as(C.POINTER(C.c_double))), "issue probe")
+print("DFMA/clk/SM with k integer IMADs interleaved per DFMA (k=0..3):", np.round(out4 * 1e12 / clk / sms, 2))

@@ -45,6 +45,23 @@ def test_log_pos_fp64():
     assert got[-1] == -np.inf and got[-7] == 0.0
 
 
+def test_log_table_fp64():
+    """The kernel's table-driven log: absolute error <= 5e-16 on the range a mixture row sum lives in
+    (what a SUM of logs needs), relative error <= 1e-13 next to 1, exact at 1; full range via the slow path."""
+    rng = np.random.RandomState(3)
+    x = np.concatenate([rng.uniform(1e-3, 8.0, 300000), 1.0 + rng.uniform(-4e-3, 4e-3, 100000),
+                        1.0 + rng.uniform(-1e-9, 1e-9, 1000), 10.0 ** rng.uniform(-300, 300, 100000),
+                        [1.0, 2.0, 0.5, 1e-310, 0.0]])
+    got = run(4, x)
+    with np.errstate(divide="ignore"):
+        want = np.log(x)
+    mid = (x > 1e-3) & (x < 8.0)
+    assert np.abs(got[mid] - want[mid]).max() < 1e-15
+    nz = np.isfinite(want) & (want != 0)
+    assert (np.abs(got[nz] - want[nz]) / np.abs(want[nz])).max() < 1e-13
+    assert got[-5] == 0.0 and got[-1] == -np.inf
+
+
 def test_fp32_variants():
     rng = np.random.RandomState(2)
     e = rng.uniform(0, 80, 100000)
