@@ -396,13 +396,22 @@ def main():
         chain_kw.update(dimension=prm["p"] + 1, initial_theta=np.concatenate([[1.0], shard["beta"]]))
     elif kind == "boltzmann":
         chain_kw.update(dimension=prm["D"])
-    barrier()
-    cres = pf_chain.run_chain(eng, **chain_kw)
-    torch.cuda.synchronize()
-    chain_info = {"steps_per_sec": cres.chain_steps_per_sec, "levels": int(cres.stats["levels"]),
-                  "engine_calls": int(cres.stats["engine_calls"]), "nodes_scored": int(cres.stats["nodes_scored"]),
-                  "frontier": B, "accept_rate": float(cres.accept[1:].mean()) if len(cres.accept) > 1 else None,
-                  "seconds": cres.stats["seconds"], "eval_seconds": cres.stats["eval_seconds"]}
+    def chain_run(**kw):
+        barrier()
+        r = pf_chain.run_chain(eng, **chain_kw, **kw)
+        torch.cuda.synchronize()
+        return {"steps_per_sec": r.chain_steps_per_sec, "levels": int(r.stats["levels"]),
+                "engine_calls": int(r.stats["engine_calls"]), "node_passes": int(r.stats["nodes_scored"]),
+                "node_item_evals": int(r.stats["items_scored"]), "dropped_early": int(r.stats["abandoned"]),
+                "frontier": B, "accept_rate": float(r.accept[1:].mean()) if len(r.accept) > 1 else None,
+                "seconds": r.stats["seconds"], "eval_seconds": r.stats["eval_seconds"]}
+
+    chain_info = chain_run()  # nodes scored whole: one kernel pass per scheduling burst
+    n_items = eng.data_size * world if kind in ("mixture", "blasso") and world > 1 else eng.data_size
+    if eng.data_size >= 16 and world == 1:
+        # predictive mode (the reference's -b / -y 0): a probe batch of 1/16 of the items, then the rest,
+        # only for the nodes the tree still believes in
+        chain_info["predictive"] = chain_run(batch_items=max(1, eng.data_size // 16), update_style=0)
 
     if rank == 0:
         pk, pk_src = peaks()

@@ -36,7 +36,8 @@ class ChainConfig(C.Structure):
         ("frontier", C.c_uint32), ("scheduling_policy", C.c_uint32), ("chain_length", C.c_uint64),
         ("correlation", C.c_double), ("reassign_ratio", C.c_double), ("dimension", C.c_uint32),
         ("threshold", C.c_int32), ("verbose", C.c_int32), ("print_tsv", C.c_int32), ("seed", C.c_uint32),
-        ("deferred_proposals", C.c_uint32), ("tau", C.c_double), ("initial_theta", C.POINTER(C.c_double)),
+        ("deferred_proposals", C.c_uint32), ("batch_items", C.c_uint64),
+        ("update_style", C.c_uint32), ("reserved2", C.c_uint32), ("tau", C.c_double), ("initial_theta", C.POINTER(C.c_double)),
     ]
 
 
@@ -45,7 +46,8 @@ class ChainStats(C.Structure):
     _fields_ = [
         ("levels", C.c_uint64), ("rows", C.c_uint64), ("engine_calls", C.c_uint64), ("nodes_scored", C.c_uint64),
         ("max_frontier", C.c_uint64), ("allocated_nodes", C.c_uint64), ("recycled_nodes", C.c_uint64),
-        ("seconds", C.c_double), ("eval_seconds", C.c_double),
+        ("seconds", C.c_double), ("eval_seconds", C.c_double), ("items_scored", C.c_uint64),
+        ("abandoned", C.c_uint64),
     ]
 
 
@@ -54,6 +56,7 @@ ROW_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_int, C.c_double, _dp, C.c
 JOB_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_char_p, C.c_uint64, C.c_uint64,
                      C.c_uint64, C.c_double, _dp, C.c_uint32)
 EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, _dp, _dp, _dp)
+RANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, _dp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), _dp, _dp)
 
 # every symbol include/pfetch.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -68,7 +71,7 @@ SYMBOLS = {
     "pf_chain_run": (C.c_int, [C.c_void_p, C.POINTER(ChainConfig), ROW_FN, JOB_FN, C.c_void_p,
                                C.POINTER(ChainStats)]),
     "pf_chain_run_with_evaluator": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(ChainConfig),
-                                              EVAL_FN, C.c_void_p, ROW_FN, JOB_FN, C.c_void_p,
+                                              EVAL_FN, RANGE_FN, C.c_void_p, ROW_FN, JOB_FN, C.c_void_p,
                                               C.POINTER(ChainStats)]),
     "pf_eval_frontier": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp]),
     "pf_eval_frontier_range": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_uint64, C.c_uint64,

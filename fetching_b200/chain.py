@@ -14,7 +14,7 @@ from typing import Callable, List, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import EVAL_FN, JOB_FN, ROW_FN, ChainConfig, ChainStats, check
+from ._lib import EVAL_FN, JOB_FN, RANGE_FN, ROW_FN, ChainConfig, ChainStats, check
 
 
 @dataclass
@@ -36,12 +36,13 @@ class ChainResult:
 
 
 def _config(frontier, chain_length, policy, correlation, reassign_ratio, dimension, threshold, verbose, print_tsv,
-            seed, tau, initial_theta, deferred=False):
+            seed, tau, initial_theta, deferred=False, batch_items=0, update_style=1):
     cfg = ChainConfig()
     cfg.frontier, cfg.scheduling_policy, cfg.chain_length = frontier, policy, chain_length
     cfg.correlation, cfg.reassign_ratio, cfg.dimension = correlation, reassign_ratio, dimension
     cfg.threshold, cfg.verbose, cfg.print_tsv, cfg.seed, cfg.tau = int(threshold), int(verbose), int(print_tsv), seed, tau
     cfg.deferred_proposals = int(deferred)
+    cfg.batch_items, cfg.update_style = int(batch_items), int(update_style)
     keep = None
     if initial_theta is not None:
         keep = np.ascontiguousarray(initial_theta, dtype=np.float64)
@@ -76,10 +77,12 @@ def _result(rows, jobs, st):
 def run_chain(engine, chain_length: int = 100, frontier: int = 8, *, policy: int = 2, correlation: float = 0.99,
               reassign_ratio: float = 1.1, dimension: int = 1, threshold: bool = False, verbose: bool = False,
               print_tsv: bool = False, seed: int = 0, tau: float = 5.0, initial_theta=None,
-              trace_jobs: bool = False, deferred_proposals: bool = False) -> ChainResult:
-    """Defaults follow tree.cc:45-48 (-l 100 -r 1.1 -c 0.99 -d 1 -s 2)."""
+              trace_jobs: bool = False, deferred_proposals: bool = False, batch_items: int = 0,
+              update_style: int = 1) -> ChainResult:
+    """Defaults follow tree.cc:45-48 (-l 100 -r 1.1 -c 0.99 -d 1 -s 2).  batch_items > 0 turns on partial
+    updates (the reference's -b / -y), i.e. predictive scheduling from partial sums."""
     cfg, _keep = _config(frontier, chain_length, policy, correlation, reassign_ratio, dimension, threshold, verbose,
-                         print_tsv, seed, tau, initial_theta, deferred_proposals)
+                         print_tsv, seed, tau, initial_theta, deferred_proposals, batch_items, update_style)
     rows, jobs, row_cb, job_cb = _collect(trace_jobs)
     st = ChainStats()
     check(_lib.load().pf_chain_run(engine._h, C.byref(cfg), row_cb, job_cb, None, C.byref(st)), "pf_chain_run")
@@ -91,11 +94,12 @@ def run_chain_with_evaluator(model: int, dim: int, components: int, data_size: i
                              policy: int = 2, correlation: float = 0.99, reassign_ratio: float = 1.1,
                              dimension: int = 1, threshold: bool = False, verbose: bool = False, seed: int = 0,
                              tau: float = 5.0, initial_theta=None, trace_jobs: bool = False,
-                             deferred_proposals: bool = False) -> ChainResult:
+                             deferred_proposals: bool = False, batch_items: int = 0, update_style: int = 1,
+                             range_evaluator=None) -> ChainResult:
     """Same tree / sampler / hand-off, frontier scored by `evaluator(thetas[B][L]) -> (sum[B], sum_sq[B])`.
     No GPU involved: used to exercise the host logic (the CPU test-suite passes the oracle here)."""
     cfg, _keep = _config(frontier, chain_length, policy, correlation, reassign_ratio, dimension, threshold, verbose,
-                         False, seed, tau, initial_theta, deferred_proposals)
+                         False, seed, tau, initial_theta, deferred_proposals, batch_items, update_style)
     rows, jobs, row_cb, job_cb = _collect(trace_jobs)
     theta_len = {1: dim + dim * (dim + 1) // 2, 2: 1, 3: dim, 4: dim * components, 5: dim + 1}[model]
 
@@ -106,8 +110,17 @@ def run_chain_with_evaluator(model: int, dim: int, components: int, data_size: i
         np.ctypeslib.as_array(q_out, shape=(B,))[:] = q
         return 0
 
+    def on_range(_u, B, thetas, first, count, order, s_out, q_out):
+        th = np.ctypeslib.as_array(thetas, shape=(B, theta_len))
+        od = np.ctypeslib.as_array(order, shape=(B, 2))
+        s, q = range_evaluator(th, int(first), int(count), od)
+        np.ctypeslib.as_array(s_out, shape=(B,))[:] = s
+        np.ctypeslib.as_array(q_out, shape=(B,))[:] = q
+        return 0
+
     st = ChainStats()
+    range_cb = RANGE_FN(on_range) if range_evaluator is not None else RANGE_FN()
     check(_lib.load().pf_chain_run_with_evaluator(model, dim, components, data_size, C.byref(cfg), EVAL_FN(on_eval),
-                                                  None, row_cb, job_cb, None, C.byref(st)),
+                                                  range_cb, None, row_cb, job_cb, None, C.byref(st)),
           "pf_chain_run_with_evaluator")
     return _result(rows, jobs, st)

@@ -91,6 +91,29 @@ struct FrontierEvaluator {
                              : fn(user, (uint32_t) jobs.size(), thetas.data(), sum.data(), sum_sq.data());
         if (r != PF_OK && status == PF_OK) status = r;
     }
+    // items [first, first + count) of every node; the normal target walks them in each node's own order
+    void range(const std::vector<FrontierJob>& jobs, std::size_t first, std::size_t count, std::vector<double>& sum,
+               std::vector<double>& sum_sq) {
+        thetas.assign(jobs.size() * (std::size_t) theta_len, 0.0);
+        order.assign(jobs.size() * 2, 0);
+        for (std::size_t i = 0; i < jobs.size(); ++i) {
+            load_doubles(jobs[i].theta, &thetas[i * theta_len], theta_len);
+            order[2 * i] = jobs[i].order_stride;
+            order[2 * i + 1] = jobs[i].order_start;
+        }
+        int r;
+        if (engine)
+            r = pf_eval_frontier_range(engine, (uint32_t) jobs.size(), thetas.data(), first, count,
+                                       ordered ? order.data() : nullptr, sum.data(), sum_sq.data());
+        else
+            r = range_fn ? range_fn(user, (uint32_t) jobs.size(), thetas.data(), first, count, order.data(), sum.data(),
+                                    sum_sq.data())
+                         : PF_ERR_UNSUPPORTED;
+        if (r != PF_OK && status == PF_OK) status = r;
+    }
+    pf_chain_range_fn range_fn = nullptr;
+    bool ordered = false;
+    std::vector<uint64_t> order;
 };
 
 struct ChainTarget {  // what is being sampled and who scores it
@@ -100,6 +123,7 @@ struct ChainTarget {  // what is being sampled and who scores it
     pf_engine* engine;
     pf_chain_eval_fn fn;
     void* eval_user;
+    pf_chain_range_fn range_fn;
 };
 
 template <class Executor>
@@ -117,9 +141,12 @@ static int run_chain(const ChainTarget& tg, Executor& ex, const pf_chain_config&
     if (cfg.print_tsv) hook.SamplerType::notify(tree, 0, 0, std::string(), false);  // the header line
 
     FrontierEvaluator eval{tg.engine, tg.fn, tg.eval_user, theta_len};
+    eval.range_fn = tg.range_fn;
+    eval.ordered = tg.model == PF_MODEL_NORMAL;
     JobTrace trace{job, user, theta_len, {}};
     FrontierCommunicator<SpecTree, Executor, HostTypes, FrontierEvaluator, JobTrace> comm(
-        tree, ex, eval, workers, data_size, &trace, cfg.deferred_proposals == 0);
+        tree, ex, eval, workers, data_size, &trace, cfg.deferred_proposals == 0, (std::size_t) cfg.batch_items,
+        (int) cfg.update_style);
     SpecTree::run_behavior rb;
     rb.quiet = cfg.verbose == 0;
     const auto t0 = std::chrono::steady_clock::now();
@@ -135,6 +162,8 @@ static int run_chain(const ChainTarget& tg, Executor& ex, const pf_chain_config&
         stats->allocated_nodes = tree.allocated_nodes();
         stats->recycled_nodes = tree.recycled_nodes();
         stats->rows = hook.rows();
+        stats->items_scored = comm.stats().items_scored;
+        stats->abandoned = comm.stats().abandoned + comm.stats().skipped;
     }
     return eval.status;
 }
@@ -175,14 +204,14 @@ extern "C" PF_API int pf_chain_run(pf_engine* engine, const pf_chain_config* cfg
     if (!engine || !cfg) return PF_ERR_INVALID;
     pf::host::ChainTarget tg{pf_engine_model(engine), pf_engine_dim(engine), pf_engine_components(engine),
                              pf_engine_theta_len(engine), (std::size_t) pf_engine_data_size(engine), engine, nullptr,
-                             nullptr};
+                             nullptr, nullptr};
     return dispatch_chain(tg, cfg, row, job, user, stats);
 }
 
 extern "C" PF_API int pf_chain_run_with_evaluator(int model, uint32_t dim, uint32_t components, uint64_t data_size,
-                                                  const pf_chain_config* cfg, pf_chain_eval_fn eval, void* eval_user,
-                                                  pf_chain_row_fn row, pf_chain_job_fn job, void* user,
-                                                  pf_chain_stats* stats) {
+                                                  const pf_chain_config* cfg, pf_chain_eval_fn eval,
+                                                  pf_chain_range_fn eval_range, void* eval_user, pf_chain_row_fn row,
+                                                  pf_chain_job_fn job, void* user, pf_chain_stats* stats) {
     if (!cfg || !eval || data_size == 0) return PF_ERR_INVALID;
     uint32_t theta_len = 0;
     switch (model) {
@@ -193,6 +222,8 @@ extern "C" PF_API int pf_chain_run_with_evaluator(int model, uint32_t dim, uint3
         case PF_MODEL_BLASSO: theta_len = dim + 1; break;
         default: return PF_ERR_INVALID;
     }
-    pf::host::ChainTarget tg{model, dim, components, theta_len, (std::size_t) data_size, nullptr, eval, eval_user};
+    if (cfg->batch_items && !eval_range) return PF_ERR_INVALID;
+    pf::host::ChainTarget tg{model, dim, components, theta_len, (std::size_t) data_size, nullptr, eval, eval_user,
+                             eval_range};
     return dispatch_chain(tg, cfg, row, job, user, stats);
 }

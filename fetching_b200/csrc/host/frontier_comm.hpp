@@ -11,6 +11,14 @@
 //     (accepted by the tree: master.cc:161-163,169) followed by WANTWORK.
 // Deterministic: per-rank FIFO inboxes, batch scored in hand-out order.
 //
+// BATCHED MODE (batch_items > 0): the predictive part of predictive prefetching.  Like a reference
+// worker (worker.hh:130-175) every virtual worker walks its node in batches of items and reports the
+// CUMULATIVE partial sums after each batch, so the tree can estimate branch probabilities from partial
+// evidence (master.cc:97-142), stop speculating down improbable branches, and pull workers off
+// nodes that became useless (ABANDON, masterloop.cc:70-82).  Each flush advances every active
+// worker by one batch: one evaluator.range() call per distinct item range.  Update styles as in
+// worker.hh:141-147 (FAST_SLOW / LOGARITHMIC: one probe batch, then the rest; INCREMENTAL: fixed batches).
+//
 // Generic over the tree / record types on purpose: the oracle build instantiates this same
 // header with the REFERENCE's JobTree and records and a CPU evaluator to produce the golden
 // traces that the product (SpecTree + GPU engine) must reproduce bit for bit.
@@ -31,10 +39,13 @@ struct FrontierJob {  // one node of the batch handed to the evaluator
     int rank;
     std::size_t id, generation;
     std::string theta;  // raw doubles
+    std::size_t order_stride = 1, order_start = 0;  // the node's item visiting order, when the sampler has one
 };
 
 struct FrontierStats {
     std::size_t engine_calls = 0, nodes_scored = 0, max_batch = 0, jobs = 0;
+    std::size_t items_scored = 0;  // sum over calls of nodes x items: the work actually paid for
+    std::size_t abandoned = 0, skipped = 0;
     double eval_seconds = 0.0;
 };
 
@@ -68,9 +79,12 @@ class FrontierCommunicator {
     // (like real workers), and jobs carry accept/reject paths to be replayed (worker.hh:38-47).
     // Every virtual worker owns a copy of the executor, as every reference worker does.
     FrontierCommunicator(Tree& tree, const Executor& executor, Evaluator& evaluator, int workers,
-                         std::size_t data_size, Trace* trace, bool eager_proposals = true)
+                         std::size_t data_size, Trace* trace, bool eager_proposals = true,
+                         std::size_t batch_items = 0, int update_style = 1)
         : tree_(tree), executors_(workers + 1, executor), evaluator_(evaluator), trace_(trace), data_size_(data_size),
-          eager_(eager_proposals), inbox_(workers + 1), proposals_(workers + 1), updates_(workers + 1) {
+          eager_(eager_proposals), batch_items_(batch_items >= data_size ? 0 : batch_items),
+          update_style_(update_style), inbox_(workers + 1), proposals_(workers + 1), updates_(workers + 1),
+          work_(workers + 1) {
         for (int r = 1; r <= workers; ++r) {  // worker.hh:66,74
             push(r, FC_REGISTER);
             push(r, FC_WANTWORK);
@@ -81,7 +95,12 @@ class FrontierCommunicator {
     const FrontierStats& stats() const { return stats_; }
 
     std::optional<Status> iprobe(int rank, int) {
-        if (queued_ == 0 && !batch_.empty()) flush();
+        if (queued_ == 0) {
+            if (batch_items_ == 0) {
+                if (!batch_.empty()) flush();
+            } else
+                advance();
+        }
         if (inbox_[rank].empty()) return std::nullopt;
         return Status(rank, inbox_[rank].front());
     }
@@ -118,15 +137,129 @@ class FrontierCommunicator {
             proposals_[rank].push_back(proposal);
             push(rank, FC_SETPROPOSAL);
         }
-        batch_.push_back(FrontierJob{rank, job.id, job.generation, proposal.proposal});
+        FrontierJob fj{rank, job.id, job.generation, proposal.proposal};
+        order_of(executors_[rank], fj, 0);
         ++stats_.jobs;
+        if (batch_items_ == 0)
+            batch_.push_back(fj);
+        else {  // worker.hh:130-135: cumulative sums continue from what the tree already has
+            Work& w = work_[rank];
+            w.active = true;
+            w.job = fj;
+            w.position = job_in.first_position;
+            w.sum = job_in.metric_sum;
+            w.sum_sq = job_in.metric_sum_sq;
+        }
         return Request();
     }
 
-    // Nodes are scored whole, so there is never work in progress to abandon.
-    Request isend(int, int, const AbandonInfoT&) { return Request(); }
+    // masterloop.cc:76-82 -> worker.hh:169-175: drop the node if it is still the one being worked on
+    Request isend(int rank, int, const AbandonInfoT& ab) {
+        if (batch_items_ != 0) {
+            Work& w = work_[rank];
+            if (w.active && w.job.id == ab.id && w.job.generation == ab.generation) {
+                w.active = false;
+                ++stats_.abandoned;
+                push(rank, FC_WANTWORK);
+            }
+        }
+        return Request();
+    }
 
   private:
+    struct Work {  // what a virtual worker is in the middle of (batched mode)
+        bool active = false;
+        FrontierJob job;
+        std::size_t position = 0, batch = 0;
+        double sum = 0.0, sum_sq = 0.0;
+    };
+
+    // executors that define a visiting order expose order(); the others are walked in natural order
+    template <class E>
+    static auto order_of(const E& ex, FrontierJob& fj, int) -> decltype(ex.order().stride(), void()) {
+        fj.order_stride = ex.order().stride();
+        fj.order_start = ex.order().start();
+    }
+    template <class E>
+    static void order_of(const E&, FrontierJob&, long) {}
+
+    // One step of every active worker (batched mode): its next item range, grouped so that workers at the
+    // same range are scored by one evaluator call.
+    void advance() {
+        struct Group {
+            std::size_t first, count;
+            std::vector<int> ranks;
+        };
+        std::vector<Group> groups;
+        for (int r = 1; r < (int) work_.size(); ++r) {
+            Work& w = work_[r];
+            if (!w.active) continue;
+            // a node the tree has already deleted or decided against is not worth more work
+            // (MasterTester makes the same check, testmaster.cc:170); the worker asks for new work
+            auto* n = tree_.node(w.job.id);
+            if (!n || n->is_dead() || n->complete()) {
+                w.active = false;
+                ++stats_.skipped;
+                push(r, FC_WANTWORK);
+                continue;
+            }
+            std::size_t stop;
+            if (update_style_ == 1 || w.position == 0)  // worker.hh:141-147
+                stop = w.position + batch_items_;
+            else
+                stop = data_size_;
+            if (stop > data_size_) stop = data_size_;
+            const std::size_t count = stop - w.position;
+            Group* g = nullptr;
+            for (Group& c : groups)
+                if (c.first == w.position && c.count == count) g = &c;
+            if (!g) {
+                groups.push_back(Group{w.position, count, {}});
+                g = &groups.back();
+            }
+            g->ranks.push_back(r);
+        }
+        for (Group& g : groups) {
+            batch_.clear();
+            for (int r : g.ranks) batch_.push_back(work_[r].job);
+            const std::size_t n = batch_.size();
+            sum_.assign(n, 0.0);
+            sum_sq_.assign(n, 0.0);
+            const auto t0 = std::chrono::steady_clock::now();
+            evaluator_.range(batch_, g.first, g.count, sum_, sum_sq_);
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            stats_.eval_seconds += dt;
+            ++stats_.engine_calls;
+            stats_.nodes_scored += n;
+            stats_.items_scored += n * g.count;
+            if (n > stats_.max_batch) stats_.max_batch = n;
+            for (std::size_t i = 0; i < n; ++i) {
+                const int r = g.ranks[i];
+                Work& w = work_[r];
+                w.sum += sum_[i];
+                w.sum_sq += sum_sq_[i];
+                w.position = g.first + g.count;
+                MetricChangeT u;
+                u.id = w.job.id;
+                u.first_position = 0;  // cumulative since item 0 (worker.hh:131)
+                u.last_position = w.position;
+                u.metric_sum = w.sum;
+                u.metric_sum_sq = w.sum_sq;
+                u.step_time = dt / (double) n;
+                u.step_count = g.count;
+                u.abandon = w.position == data_size_;
+                u.worker_wait_time = 0.0;
+                updates_[r].push_back(u);
+                push(r, FC_UPDATE);
+                if (u.abandon) {
+                    w.active = false;
+                    push(r, FC_WANTWORK);
+                }
+            }
+        }
+        batch_.clear();
+    }
+
     void push(int rank, int tag) {
         inbox_[rank].push_back(tag);
         ++queued_;
@@ -146,6 +279,7 @@ class FrontierCommunicator {
         stats_.eval_seconds += dt;
         ++stats_.engine_calls;
         stats_.nodes_scored += n;
+        stats_.items_scored += n * data_size_;
         if (n > stats_.max_batch) stats_.max_batch = n;
         for (std::size_t i = 0; i < n; ++i) {
             MetricChangeT u;
@@ -171,10 +305,13 @@ class FrontierCommunicator {
     Trace* trace_;
     std::size_t data_size_;
     bool eager_;
+    std::size_t batch_items_;
+    int update_style_;
     std::vector<std::deque<int>> inbox_;
     std::vector<std::deque<ProposalInfoT>> proposals_;
     std::vector<std::deque<MetricChangeT>> updates_;
     std::vector<FrontierJob> batch_;
+    std::vector<Work> work_;
     std::vector<double> sum_, sum_sq_;
     std::size_t queued_ = 0;
     FrontierStats stats_;

@@ -6,7 +6,9 @@
 //
 // Same flags with the same meaning and defaults (tree.cc:45-48,62-110); `-n NP` replaces
 // `mpirun -np NP` (NP - 1 = nodes scored per kernel pass; default 2 as in the README example).
-// -b / -u / -y are accepted for compatibility: nodes are scored whole, there are no batches.
+// -b BATCH / -y STYLE turn on partial updates every BATCH items (predictive scheduling from partial sums,
+// worker.hh:141-175); the default -b 0 scores nodes whole, one kernel pass per scheduling burst.  -u is accepted
+// and ignored (it injects artificial latency in the reference).
 // stdout: the chain TSV of stype.cc:67-84; stderr: the command echo (tree.cc:145), the -p table
 // (master.cc:324-345) and the final `OK sample/s = ...` line (tree.cc:163-168).
 //
@@ -81,7 +83,7 @@ const double kMixturePos[8][8] = {
 int main(int argc, char** argv) {
     using namespace pf::host;
     const char* sampler_name = nullptr;
-    int np = 2, device = 0, chain_length = 100, batch_size = 1000, usleep_time = 0, dimension = 1;
+    int np = 2, device = 0, chain_length = 100, batch_size = 0, usleep_time = 0, dimension = 1;
     double reassign_ratio = 1.1, correlation = 0.99;
     bool threshold = false, quiet = true;
     int update_style = 1, scheduling_policy = 2;
@@ -208,6 +210,8 @@ int main(int argc, char** argv) {
     cfg.threshold = threshold;
     cfg.verbose = !quiet;
     cfg.print_tsv = 1;
+    cfg.batch_items = batch_size > 0 ? (uint64_t) batch_size : 0;
+    cfg.update_style = (uint32_t) update_style;
     pf_chain_stats st;
     memset(&st, 0, sizeof st);
     const int rc = pf_chain_run(engine, &cfg, nullptr, nullptr, nullptr, &st);
@@ -217,8 +221,10 @@ int main(int argc, char** argv) {
     fflush(stdout);
     fprintf(stderr, "OK sample/s = %-7.3f samples = %-6d seconds = %-7.3f N = %d\n", chain_length / (toc - tic),
             chain_length, toc - tic, np);  // tree.cc:163-168
-    fprintf(stderr, "# chain only: %.3f sample/s, %llu kernel passes, %llu nodes scored, largest frontier %llu\n",
+    fprintf(stderr, "# chain only: %.3f sample/s, %llu engine calls, %llu node passes, %llu node x item evaluations, "
+                    "%llu nodes dropped early, largest frontier %llu\n",
             st.seconds > 0 ? st.levels / st.seconds : 0.0, (unsigned long long) st.engine_calls,
-            (unsigned long long) st.nodes_scored, (unsigned long long) st.max_frontier);
+            (unsigned long long) st.nodes_scored, (unsigned long long) st.items_scored,
+            (unsigned long long) st.abandoned, (unsigned long long) st.max_frontier);
     return rc == PF_OK ? 0 : 1;
 }

@@ -170,6 +170,10 @@ typedef struct pf_chain_config {
     uint32_t seed;               /* mixture: seed of first_proposal (pymixture.py:71) */
     uint32_t deferred_proposals; /* 0: the tree learns a proposal as soon as it is made (MasterTester-like);
                                     1: only when the master reads SETPROPOSAL, so jobs carry replay paths */
+    uint64_t batch_items;        /* -b: 0 = score nodes whole; > 0 = partial updates every batch_items items, which
+                                    feed the predictive scheduler and allow abandoning (worker.hh:141-175) */
+    uint32_t update_style;       /* -y: 0 fast/slow, 1 incremental, 2 logarithmic (protocol.hh:26-30) */
+    uint32_t reserved2;
     double tau;                  /* lasso prior rate (0 -> 5.0, pyblasso.py:32) */
     const double* initial_theta; /* lasso: optional initial (sigma, beta); NULL -> (1, 0, ..., 0) */
 } pf_chain_config;
@@ -182,6 +186,8 @@ typedef struct pf_chain_stats {
     uint64_t max_frontier;
     uint64_t allocated_nodes, recycled_nodes;
     double seconds, eval_seconds;
+    uint64_t items_scored;  /* sum over engine calls of nodes x items: the work paid for */
+    uint64_t abandoned;     /* nodes dropped before completion (ABANDON, or found dead) */
 } pf_chain_stats;
 
 typedef void (*pf_chain_row_fn)(void* user, uint64_t depth, int accept, double metric_sum, const double* theta,
@@ -199,10 +205,13 @@ PF_API int pf_chain_run(pf_engine* e, const pf_chain_config* cfg, pf_chain_row_f
  * Needs no device; it exists so the host logic can be exercised anywhere (the CPU test-suite
  * plugs the oracle in here) and so another evaluator can sit behind the same tree. */
 typedef int (*pf_chain_eval_fn)(void* user, uint32_t B, const double* thetas, double* sum, double* sum_sq);
+/* items [first, first + count); order[2b], order[2b+1] = stride, start of node b (normal target), else (1, 0) */
+typedef int (*pf_chain_range_fn)(void* user, uint32_t B, const double* thetas, uint64_t first, uint64_t count,
+                                 const uint64_t* order, double* sum, double* sum_sq);
 PF_API int pf_chain_run_with_evaluator(int model, uint32_t dim, uint32_t components, uint64_t data_size,
-                                       const pf_chain_config* cfg, pf_chain_eval_fn eval, void* eval_user,
-                                       pf_chain_row_fn row, pf_chain_job_fn job, void* user,
-                                       pf_chain_stats* stats);
+                                       const pf_chain_config* cfg, pf_chain_eval_fn eval,
+                                       pf_chain_range_fn eval_range, void* eval_user, pf_chain_row_fn row,
+                                       pf_chain_job_fn job, void* user, pf_chain_stats* stats);
 
 /* Options. */
 enum pf_option {

@@ -138,6 +138,10 @@ FRONTIER_TRACES = {
     "frontier_trace_normal_W64_const.tsv": ["frontier", "normal", "-W", "64", "-d", "10000", "-l", "60", "-s", "1"],
     "frontier_trace_boltzmann_W8.tsv": ["frontier", "boltzmann", "-W", "8", "-d", "10000", "-l", "80"],
     "frontier_trace_boltzmann_W5_deferred.tsv": ["frontier", "boltzmann", "-W", "5", "-d", "10000", "-l", "60", "--deferred"],
+    # batched mode: partial updates feed the predictive scheduler, workers get abandoned (worker.hh:141-175)
+    "frontier_trace_normal_W8_b1000_fastslow.tsv": ["frontier", "normal", "-W", "8", "-d", "10000", "-l", "80", "-b", "1000", "-y", "0"],
+    "frontier_trace_normal_W16_b2000_incremental.tsv": ["frontier", "normal", "-W", "16", "-d", "10000", "-l", "40", "-b", "2000", "-y", "1"],
+    "frontier_trace_boltzmann_W8_b1000_fastslow.tsv": ["frontier", "boltzmann", "-W", "8", "-d", "10000", "-l", "60", "-b", "1000", "-y", "0"],
 }
 
 

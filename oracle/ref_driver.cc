@@ -162,6 +162,24 @@ struct RefEvaluator {  // what MasterTester::check_update does per node (testmas
             sq[i] = q;
         }
     }
+    // items [first, first + count) in each node's own visiting order (what a worker does between two
+    // updates, worker.hh:148-155)
+    void range(const std::vector<pf::host::FrontierJob>& jobs, size_t first, size_t count, std::vector<double>& sum,
+               std::vector<double>& sq) {
+        for (size_t i = 0; i != jobs.size(); ++i) {
+            JobNode* jn = tree->node(jobs[i].id);
+            JobInfo job;
+            job.state = JobInfo::s_has_proposal;
+            job.theta = jobs[i].theta;
+            job.random_position = jn ? jn->random_position() : 0;
+            (void) sampler.load(job);
+            sampler.prepare();
+            double s = 0, q = 0;
+            sampler.evaluate_many(first, count, s, q);
+            sum[i] = s;
+            sq[i] = q;
+        }
+    }
 };
 
 template <typename T>
@@ -175,7 +193,7 @@ class TraceHook : public SamplerType {
 
 template <typename S, typename T>
 int run_frontier(const S& sampler, size_t workers, size_t data_size, size_t levels, size_t policy, double reassign,
-                 bool eager) {
+                 bool eager, size_t batch, int style) {
     TraceHook<T> hook;
     tree = new JobTree(workers + 1, levels, &hook, policy, 0.99, 1);
     tree->set_reassign_ratio(reassign);
@@ -184,10 +202,11 @@ int run_frontier(const S& sampler, size_t workers, size_t data_size, size_t leve
     RefEvaluator<S> evaluator{sampler, data_size};
     RefTrace trace;
     typedef pf::host::FrontierCommunicator<JobTree, S, RefTypes, RefEvaluator<S>, RefTrace> Comm;
-    Comm comm(*tree, sampler, evaluator, (int) workers, data_size, &trace, eager);
+    Comm comm(*tree, sampler, evaluator, (int) workers, data_size, &trace, eager, batch, style);
     tree->run_master<Comm, typename Comm::Request, typename Comm::Status>(comm, JobTree::run_behavior().quiet(true));
-    printf("# levels %zu engine_calls %zu nodes_scored %zu max_batch %zu\n", tree->completed_depth(),
-           comm.stats().engine_calls, comm.stats().nodes_scored, comm.stats().max_batch);
+    printf("# levels %zu engine_calls %zu nodes_scored %zu max_batch %zu items_scored %zu abandoned %zu skipped %zu\n",
+           tree->completed_depth(), comm.stats().engine_calls, comm.stats().nodes_scored, comm.stats().max_batch,
+           comm.stats().items_scored, comm.stats().abandoned, comm.stats().skipped);
     return 0;
 }
 
@@ -196,10 +215,14 @@ int cmd_frontier(int argc, char** argv) {
     size_t workers = 8, data_size = 10000, levels = 50, policy = PREDICTIVE;
     double reassign = 1.1;
     bool eager = true;
+    size_t batch = 0;
+    int style = 1;
     for (int i = 0; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
         if (a == "--deferred") eager = false;
+        else if (a == "-b") batch = strtoull(next(), 0, 0);
+        else if (a == "-y") style = (int) strtol(next(), 0, 0);
         else if (a == "-W") workers = strtoull(next(), 0, 0);
         else if (a == "-d") data_size = strtoull(next(), 0, 0);
         else if (a == "-l") levels = strtoull(next(), 0, 0);
@@ -208,10 +231,10 @@ int cmd_frontier(int argc, char** argv) {
         else sampler_name = argv[i];
     }
     if (strcmp(sampler_name, "boltzmann") == 0)
-        return run_frontier<BoltzmannSampler, double>(BoltzmannSampler(), workers, data_size, levels, policy, reassign, eager);
+        return run_frontier<BoltzmannSampler, double>(BoltzmannSampler(), workers, data_size, levels, policy, reassign, eager, batch, style);
     double* data = normal_dataset(data_size);
     NormalSampler<2> sampler(data, data_size);
-    return run_frontier<NormalSampler<2>, NormalTheta<2> >(sampler, workers, data_size, levels, policy, reassign, eager);
+    return run_frontier<NormalSampler<2>, NormalTheta<2> >(sampler, workers, data_size, levels, policy, reassign, eager, batch, style);
 }
 
 struct EvalHeader {

@@ -22,6 +22,9 @@ TRACES = {
     "frontier_trace_normal_W64_const.tsv": dict(model="normal", frontier=64, levels=60, policy=1),
     "frontier_trace_boltzmann_W8.tsv": dict(model="boltzmann", frontier=8, levels=80),
     "frontier_trace_boltzmann_W5_deferred.tsv": dict(model="boltzmann", frontier=5, levels=60, deferred=True),
+    "frontier_trace_normal_W8_b1000_fastslow.tsv": dict(model="normal", frontier=8, levels=80, batch=1000, style=0),
+    "frontier_trace_normal_W16_b2000_incremental.tsv": dict(model="normal", frontier=16, levels=40, batch=2000, style=1),
+    "frontier_trace_boltzmann_W8_b1000_fastslow.tsv": dict(model="boltzmann", frontier=8, levels=60, batch=1000, style=0),
 }
 
 
@@ -54,15 +57,24 @@ def oracle_run(orc, cfg, **extra):
     if cfg["model"] == "normal":
         data = orc.normal_dataset(10000)
         ev = lambda th: orc.normal_frontier(data, th)
+
+        def ev_range(th, first, count, order):  # each node in its own StrideIndex order, like a reference worker
+            out = np.array([orc.normal_eval(data, t, int(o[0]), int(o[1]), first, count) for t, o in zip(th, order)])
+            return out[:, 0], out[:, 1]
         model, dim = _lib.MODEL_NORMAL, 2
     else:
         def ev(th):
             out = np.array([orc.boltzmann_scalar_eval(float(t[0]), 10000) for t in th])
             return out[:, 0], out[:, 1]
+
+        def ev_range(th, first, count, order):
+            out = np.array([orc.boltzmann_scalar_eval(float(t[0]), count) for t in th])
+            return out[:, 0], out[:, 1]
         model, dim = _lib.MODEL_BOLTZMANN_SCALAR, 1
     return chain.run_chain_with_evaluator(model, dim, 0, 10000, ev, chain_length=cfg["levels"], frontier=cfg["frontier"],
                                           policy=cfg.get("policy", 2), deferred_proposals=cfg.get("deferred", False),
-                                          trace_jobs=True, **extra)
+                                          batch_items=cfg.get("batch", 0), update_style=cfg.get("style", 1),
+                                          range_evaluator=ev_range, trace_jobs=True, **extra)
 
 
 @pytest.mark.parametrize("name", sorted(TRACES))
@@ -117,3 +129,15 @@ def test_native_mixture_and_lasso_chains_run_and_are_frontier_invariant(orc):
     assert np.all(runs[0].theta[:, 0] > 0)  # sigma stays positive (pyblasso.py:117-121)
     for j in runs[1].jobs:  # log_prior travels with the proposal (python.cc:168-176 -> pyblasso.py:123-133)
         assert abs(j[7] - orc.blasso_log_prior(j[8])) <= 1e-12 * abs(j[7])
+
+
+def test_predictive_partial_evaluation_saves_work_and_keeps_the_chain(orc):
+    """Batched mode (the reference's -b / -y): partial sums drive the predictive scheduler and useless
+    nodes are abandoned, so far fewer (node x item) evaluations buy the same chain."""
+    whole = oracle_run(orc, dict(model="normal", frontier=16, levels=120))
+    part = oracle_run(orc, dict(model="normal", frontier=16, levels=120, batch=1000, style=0))
+    assert np.array_equal(whole.theta[:121], part.theta[:121]) and np.array_equal(whole.accept[:121], part.accept[:121])
+    assert np.max(np.abs(whole.metric_sum[:121] - part.metric_sum[:121]) / np.abs(whole.metric_sum[:121])) < 1e-12
+    assert whole.stats["items_scored"] == whole.stats["nodes_scored"] * 10000
+    assert part.stats["items_scored"] < 0.5 * whole.stats["items_scored"]
+    assert part.stats["abandoned"] > 0

@@ -31,8 +31,10 @@ def test_gpu_chain_matches_reference_trace(fb, orc, name):
     with engine_for(fb, orc, cfg["model"]) as e:
         launches = e.launch_count
         res = chain.run_chain(e, chain_length=cfg["levels"], frontier=cfg["frontier"], policy=cfg.get("policy", 2),
-                              deferred_proposals=cfg.get("deferred", False), trace_jobs=True)
-        assert e.launch_count - launches == res.stats["engine_calls"]  # one kernel pass per scheduling burst
+                              deferred_proposals=cfg.get("deferred", False), trace_jobs=True,
+                              batch_items=cfg.get("batch", 0), update_style=cfg.get("style", 1))
+        if not cfg.get("batch"):
+            assert e.launch_count - launches == res.stats["engine_calls"]  # one kernel pass per scheduling burst
     check_against_trace(res, os.path.join(GOLD, name))
 
 
@@ -130,3 +132,15 @@ def test_cli_prints_the_reference_chain(orc):
         assert abs(float(f[3]) - float(g[2])) <= 1e-10 * abs(float(g[2])) + 1e-5  # printed with 5 decimals
     assert "OK sample/s =" in p.stderr and "#depth last_executor allocated_nodes" in p.stderr
     assert p.stderr.startswith("# 0 = ")
+
+
+def test_gpu_predictive_mode_on_mixture(fb, orc):
+    """Partial updates on the GPU path (pf_eval_frontier_range per batch): same chain, much less work."""
+    from fetching_b200 import chain, models
+    data, pos = models.mixture_dataset(200000, 8, 2, seed=3)
+    with fb.FrontierEngine.mixture(data, 8, 1000) as e:
+        whole = chain.run_chain(e, chain_length=60, frontier=16, dimension=16)
+        part = chain.run_chain(e, chain_length=60, frontier=16, dimension=16, batch_items=20, update_style=0)
+    assert np.array_equal(whole.theta[:61], part.theta[:61]) and np.array_equal(whole.accept[:61], part.accept[:61])
+    assert np.max(np.abs(whole.metric_sum[:61] - part.metric_sum[:61]) / np.abs(whole.metric_sum[:61])) < 1e-11
+    assert part.stats["items_scored"] < 0.7 * whole.stats["items_scored"]
