@@ -149,7 +149,7 @@ def algorithmic_bytes(kind, prm, rows_local, B, dtype):
 
 def fp64_view(kind, prm, rows_local, B, dtype, kern_ms, device):
     """The mixture kernel is bound by the FP64 pipe, not by HBM: report how busy
-    that pipe is.  Numerator: FP64 instructions the kernel issues per (row, node) -- 129 for K=8, d=2,
+    that pipe is.  Numerator: FP64 instructions the kernel issues per (row, node) -- 115 for K=8, d=2,
     counted in the SASS of the inner loop -- x rows x B; denominator: the FP64 FMA issue
     rate measured on this GPU by pf_debug_fp64_probe (MEASURED_PEAKS.json has no FP64 figure)."""
     if kind != "mixture" or dtype != "f64" or (prm["K"], prm["d"]) != (8, 2):
@@ -159,11 +159,11 @@ def fp64_view(kind, prm, rows_local, B, dtype, kern_ms, device):
     out = np.zeros(16)
     _lib.check(_lib.load().pf_debug_fp64_probe(device, out.ctypes.data_as(C.POINTER(C.c_double))), "fp64 probe")
     peak_tfma = float(out.max())
-    instr = 129.0 * rows_local * B
+    instr = 115.0 * rows_local * B
     achieved = instr / (kern_ms * 1e-3) / 1e12
     return {"bound": "fp64", "achieved": achieved, "peak": peak_tfma, "unit": "T FP64 instr-lanes/s (1 FMA = 1)",
             "frac": achieved / peak_tfma, "peak_tflops": 2 * peak_tfma,
-            "note": "peak measured by pf_debug_fp64_probe; 129 FP64 instr per (row,node) from the inner-loop SASS"}
+            "note": "peak measured by pf_debug_fp64_probe; 115 FP64 instr per (row,node) from the inner-loop SASS"}
 
 
 # ------------------------------------------------------------------------------------------ clocks

@@ -23,6 +23,10 @@ struct PointwiseArgs {
     unsigned long long item_rows;           // rows per item (1: every row is an item)
     unsigned int rows_per_cta;
     unsigned int B, theta_len, K;
+    // host path: `out` is mapped pinned host memory; the last CTA publishes done_seq in *done_flag after the
+    // results (system-scope fence), and the host polls the flag instead of copying + synchronising
+    unsigned long long* done_flag;
+    unsigned long long done_seq;
 };
 
 // Geometry of one launch of the streamed-matrix (lasso / dense Boltzmann) kernel.
@@ -45,6 +49,8 @@ struct MatvecArgs {
     unsigned int tile_rows;
     unsigned long long rows_per_cta;  // lasso: contiguous rows per CTA (multiple of tile_rows)
     double inv_temperature;
+    unsigned long long* done_flag;    // see PointwiseArgs
+    unsigned long long done_seq;
 };
 
 struct Engine {
@@ -67,8 +73,13 @@ struct Engine {
     void* d_betaT = nullptr;     // matvec coefficient panel
     unsigned long long* d_order = nullptr;  // [max_frontier][2] StrideIndex (stride, start) per node
     unsigned int* d_ticket = nullptr;
-    double* h_theta = nullptr;   // pinned staging
-    double* h_out = nullptr;     // pinned staging
+    double* h_theta = nullptr;   // pinned + mapped staging
+    double* d_htheta = nullptr;  // device alias of h_theta
+    double* h_out = nullptr;     // pinned + mapped: [2][64] results, then the completion flag
+    double* d_hout = nullptr;    // device alias of h_out
+    unsigned long long host_seq = 0;
+    unsigned long long* done_flag = nullptr;  // per launch: device alias of the flag, or nullptr
+    unsigned long long done_seq = 0;
     cudaStream_t stream = nullptr;
     CUtensorMap tmaps[8];        // tensor maps by box height (cached)
     unsigned tmap_rows[8] = {};

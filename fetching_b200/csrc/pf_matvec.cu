@@ -328,6 +328,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
             }
         }
     }
+    if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
+        if ((unsigned) tid < B) __threadfence_system();
+        named_bar_sync(1, MV_CONSUMERS);
+        if (tid == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
+            __threadfence_system();
+        }
+    }
     if (tid == 0) *a.ticket = 0u;
 }
 
@@ -479,6 +487,8 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     a.row_end = boltz ? e.n_rows : (first_item + n_items) * e.item_rows;
     if (a.row_end > e.n_rows) a.row_end = e.n_rows;
     a.inv_temperature = 1.0 / e.temperature;
+    a.done_flag = e.done_flag;
+    a.done_seq = e.done_seq;
     if (a.row_end <= a.row_begin) {
         cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
         return 0;

@@ -202,7 +202,11 @@ struct MixtureModel {
     }
     static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
         // exp chains kept in flight per lane (bounded by the registers the row operands need)
+#ifdef PF_MIX_G
+        constexpr int GMAX = PF_MIX_G;
+#else
         constexpr int GMAX = D <= 2 ? 8 : (D <= 4 ? 4 : 2);
+#endif
         constexpr int G = (K % GMAX == 0) ? GMAX : ((K % 2 == 0) ? 2 : 1);
         CT lp = 0;
 #pragma unroll
@@ -311,8 +315,11 @@ constexpr bool pw_two_ctas() {
 template <class M, typename T, int NPL>
 __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a);
 
+#ifndef PF_PW_BLOCKS
+#define PF_PW_BLOCKS 2
+#endif
 template <class M, typename T, int NPL>
-__global__ void __launch_bounds__(PW_THREADS, 2) pw_frontier_kernel2(const PointwiseArgs a) {
+__global__ void __launch_bounds__(PW_THREADS, PF_PW_BLOCKS) pw_frontier_kernel2(const PointwiseArgs a) {
     pw_frontier_body<M, T, NPL>(a);
 }
 
@@ -520,6 +527,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             a.out[B + tid] = Q;
         }
     }
+    if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
+        if ((unsigned) tid < B) __threadfence_system();
+        named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
+        if (tid == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
+            __threadfence_system();
+        }
+    }
     if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
 }
 
@@ -658,7 +673,7 @@ int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
         }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PW_THREADS, kPwSmem);
         if (occ < 1) occ = 1;
-        if (occ > 2) occ = 2;
+        if (occ > PF_PW_BLOCKS) occ = PF_PW_BLOCKS;
         configured = true;
     }
     PointwiseArgs a = proto;
@@ -748,6 +763,8 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     a.B = B;
     a.theta_len = e.theta_len;
     a.K = e.K;
+    a.done_flag = e.done_flag;
+    a.done_seq = e.done_seq;
     if (a.row_end <= a.row_begin) {
         cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
         return 0;
