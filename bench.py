@@ -238,6 +238,16 @@ def cpu_leg(kind, prm, B, steps, warmup, budget_s=12.0):
         what = "oracle port (loglik_oracle.c, pyblasso.py:135-141 arithmetic), OpenMP over node x item"
     elif kind == "normal":
         sample = rows_total
+        if orc.have_pf_ref():
+            # the reference's OWN NormalSampler<2>::evaluate_many (oracle/_ref/pf_ref, compiled in place from the
+            # reference sources): one thread per node, like one MPI worker per node holding the whole data set
+            reps = max(1, min(steps, 5))
+            out = json.loads(orc.run_pf_ref("normal-bench", rows_total, B, reps, min(threads, B)).strip().splitlines()[-1])
+            dt = out["seconds"] / reps
+            return dict(value=B / dt, unit="evals/s", cores=int(out["threads"]), kind="reference",
+                        sample="%d points x %d nodes per step, %d steps, %.3f s/step; reference NormalSampler<2>::"
+                               "evaluate_many (normalsampler.hh:157-165) rebuilt against oracle/shim, not the stock MPI "
+                               "binary; one thread per node" % (rows_total, B, reps, dt)), dt, reps
         shard = make_shard(kind, prm, 0, 1)
         th = make_thetas(kind, prm, shard, B)
         fn = lambda: orc.normal_frontier(shard["data"], th)
