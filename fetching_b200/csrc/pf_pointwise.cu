@@ -307,6 +307,12 @@ struct TileIter {
 // Register budget: 256 threads per CTA, so two CTAs per SM fit at up to 128 registers per thread
 // (registers are granted per pair of warps: 2 x 8 x 32 x 128 = 64K).  Models whose per-lane
 // state is large get the whole register file of one CTA instead.
+// per-item models rotate 4 tile buffers; one-row-per-item models reduce once at the end (2 x warps x nodes)
+template <class M>
+__host__ __device__ constexpr int pw_red_doubles() {
+    return (M::ITEM1 ? 2 : PW_RED_BUFS) * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+}
+
 template <class M, int NPL>
 constexpr bool pw_two_ctas() {
     return sizeof(typename M::Node) * NPL <= 160;
@@ -317,6 +323,9 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a);
 
 #ifndef PF_PW_BLOCKS
 #define PF_PW_BLOCKS 2
+#endif
+#ifndef PF_PW_MAXOCC
+#define PF_PW_MAXOCC 2  // resident CTAs per SM actually used (a third one was measured slower: 80 vs 68 us, normal B=64)
 #endif
 template <class M, typename T, int NPL>
 __global__ void __launch_bounds__(PW_THREADS, PF_PW_BLOCKS) pw_frontier_kernel2(const PointwiseArgs a) {
@@ -332,13 +341,13 @@ template <class M, typename T, int NPL>
 __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     using CT = typename M::CT;
     constexpr int DIM = M::DIM;
-    constexpr int RB = DIM * (int) sizeof(T);
-    constexpr unsigned TILE_ROWS = PW_TILE_BYTES / RB;
+    constexpr int RB_BYTES = DIM * (int) sizeof(T);
+    constexpr unsigned TILE_ROWS = PW_TILE_BYTES / RB_BYTES;
 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     double* red = reinterpret_cast<double*>(smem + PW_STAGES * PW_STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + PW_RED_DOUBLES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + pw_red_doubles<M>());
     uint64_t* empty = full + PW_STAGES;
     int* flag = reinterpret_cast<int*>(empty + PW_STAGES);
     CT* th_smem = reinterpret_cast<CT*>(reinterpret_cast<unsigned char*>(flag) + 16);  // 16-byte aligned
@@ -367,7 +376,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             while (it.next(t0, t1)) {
                 const unsigned s = t % PW_STAGES;
                 if (t >= PW_STAGES) mbar_wait(&empty[s], ((t / PW_STAGES) - 1) & 1);
-                const unsigned long long b0 = t0 * RB, b1 = t1 * RB;
+                const unsigned long long b0 = t0 * RB_BYTES, b1 = t1 * RB_BYTES;
                 const unsigned long long w0 = b0 & ~15ull, w1 = (b1 + 15ull) & ~15ull;
                 const unsigned bytes = (unsigned) (w1 - w0);
                 mbar_arrive_expect_tx(&full[s], bytes);
@@ -431,12 +440,30 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     while (it.next(t0, t1)) {
         const unsigned s = t % PW_STAGES;
         mbar_wait(&full[s], (t / PW_STAGES) & 1);
-        const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB) & 15ull);
+        const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB_BYTES) & 15ull);
         const unsigned nrows = (unsigned) (t1 - t0);
-#pragma unroll(M::ITEM1 ? 2 : 1)  // (2 rows in flight did not help the mixture: measured 9.5 vs 9.3 ms)
-        for (unsigned j = slot; j < nrows; j += nslots) {
+        // rows in flight per lane: batches of RB rows with every shared-memory load issued before the first use
+        // and no exit inside a batch (the one-row-per-item models are short dependent chains behind a 30-cycle LDS)
+        constexpr unsigned RB = M::ITEM1 ? 4 : 1;
+        unsigned j = slot;
+        if constexpr (RB > 1) {
+            for (; j + (RB - 1) * nslots < nrows; j += RB * nslots) {
+                CT x[RB][DIM];
+#pragma unroll
+                for (unsigned u = 0; u < RB; ++u) load_row<T, DIM, CT>(base + (size_t) (j + u * nslots) * RB_BYTES, x[u]);
+#pragma unroll
+                for (unsigned u = 0; u < RB; ++u)
+#pragma unroll
+                    for (int n = 0; n < NPL; ++n) {
+                        const double v = (double) M::rowlp(nd[n], x[u]);
+                        accS[n] += v;
+                        if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
+                    }
+            }
+        }
+        for (; j < nrows; j += nslots) {
             CT x[DIM];
-            load_row<T, DIM, CT>(base + (size_t) j * RB, x);
+            load_row<T, DIM, CT>(base + (size_t) j * RB_BYTES, x);
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
                 const double v = (double) M::rowlp(nd[n], x);
@@ -640,13 +667,13 @@ __global__ void debug_math_kernel(int which, const double* in, double* out, size
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr size_t kPwSmemBase = (size_t) PW_STAGES * PW_STAGE_BYTES + PW_RED_DOUBLES * sizeof(double) +
-                               2 * PW_STAGES * sizeof(uint64_t) + 32;
+constexpr size_t kPwSmemFixed = (size_t) PW_STAGES * PW_STAGE_BYTES + 2 * PW_STAGES * sizeof(uint64_t) + 32;
 
 template <class M>
 size_t pw_smem_bytes(unsigned theta_len, unsigned max_nodes) {
-    if (!M::THETA_IN_SMEM) return kPwSmemBase;
-    return kPwSmemBase + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
+    const size_t base = kPwSmemFixed + (size_t) pw_red_doubles<M>() * sizeof(double);
+    if (!M::THETA_IN_SMEM) return base;
+    return base + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
 }
 
 template <class M, typename T, int NPL>
@@ -673,7 +700,7 @@ int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
         }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PW_THREADS, kPwSmem);
         if (occ < 1) occ = 1;
-        if (occ > PF_PW_BLOCKS) occ = PF_PW_BLOCKS;
+        if (occ > PF_PW_MAXOCC) occ = PF_PW_MAXOCC;
         configured = true;
     }
     PointwiseArgs a = proto;
