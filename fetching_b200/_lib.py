@@ -18,6 +18,7 @@ STATUS = {0: "PF_OK", -1: "PF_ERR_INVALID", -2: "PF_ERR_CUDA", -3: "PF_ERR_SHAPE
 MODEL_NORMAL, MODEL_BOLTZMANN_SCALAR, MODEL_BOLTZMANN_DENSE, MODEL_MIXTURE, MODEL_BLASSO = 1, 2, 3, 4, 5
 F64, F32 = 0, 1
 OPT_ASSUME_IDENTITY_COV = 1
+OPT_NODE_SPLIT = 2
 
 
 class ModelDesc(C.Structure):

@@ -49,6 +49,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -67,6 +68,7 @@ static NcclApi* nccl_api() {
             api.CommInitRank = (decltype(api.CommInitRank)) dlsym(api.handle, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy)) dlsym(api.handle, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce)) dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather)) dlsym(api.handle, "ncclAllGather");
             api.GetErrorString = (decltype(api.GetErrorString)) dlsym(api.handle, "ncclGetErrorString");
         }
     }
@@ -75,7 +77,7 @@ static NcclApi* nccl_api() {
 }
 
 static int allreduce_out(Engine& e, double* d_out, uint32_t B, cudaStream_t s) {
-    if (!e.nccl_comm || e.nranks <= 1) return PF_OK;
+    if (!e.nccl_comm || e.nranks <= 1 || e.node_split) return PF_OK;
     NcclApi* n = nccl_api();
     if (!n) {
         set_error("NCCL library not loadable");
@@ -138,6 +140,8 @@ static void destroy(Engine* e) {
     cudaFree(e->d_part);
     cudaFree(e->d_betaT);
     cudaFree(e->d_order);
+    cudaFree(e->d_ns_send);
+    cudaFree(e->d_ns_recv);
     cudaFree(e->d_ticket);
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
@@ -349,7 +353,62 @@ static int wait_flag(Engine& e, volatile unsigned long long* flag, unsigned long
 }
 
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
+                     const uint64_t* order, double* sum, double* sum_sq);
+
+// Node-split (small data sets): the data set is replicated on every GPU, rank r scores nodes
+// [r*per, (r+1)*per) with the ordinary single-GPU kernel, and one ncclAllGather of 2*per doubles per rank hands
+// every rank every node's sums.  No data-path reduction: a node's sums come from exactly one GPU.
+static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
+                                double* sum, double* sum_sq) {
+    NcclApi* n = nccl_api();
+    if (!n || !n->AllGather) {
+        set_error("ncclAllGather not available");
+        return PF_ERR_NCCL;
+    }
+    PF_CUDA(cudaSetDevice(e.device));
+    const uint32_t G = (uint32_t) e.nranks, per = (B + G - 1) / G;
+    if (per > kMaxNodesPerPass) {
+        set_error("node split: %u nodes per rank exceed one pass (%d)", per, kMaxNodesPerPass);
+        return PF_ERR_SHAPE;
+    }
+    const uint32_t lo = (uint32_t) e.rank * per;
+    const uint32_t nloc = lo >= B ? 0 : (B - lo < per ? B - lo : per);
+    std::vector<double> s(per, 0.0), q(per, 0.0);
+    if (nloc) {
+        const bool was = e.node_split;
+        e.node_split = false;  // plain single-GPU evaluation of my slice (no collective inside)
+        const int saved = e.nranks;
+        e.nranks = 1;
+        const int r = eval_host(e, nloc, thetas + (size_t) lo * e.theta_len, first_item, n_items, nullptr, s.data(), q.data());
+        e.nranks = saved;
+        e.node_split = was;
+        if (r != PF_OK) return r;
+    }
+    // pack [sum | sum_sq] of my slice, gather everybody's
+    std::vector<double> pack(2 * (size_t) per);
+    memcpy(pack.data(), s.data(), per * 8);
+    memcpy(pack.data() + per, q.data(), per * 8);
+    PF_CUDA(cudaMemcpyAsync(e.d_ns_send, pack.data(), 2 * (size_t) per * 8, cudaMemcpyHostToDevice, e.stream));
+    ncclResult_t rc = n->AllGather(e.d_ns_send, e.d_ns_recv, 2 * (size_t) per, /*ncclDouble*/ 8, (ncclComm_t) e.nccl_comm,
+                                   e.stream);
+    if (rc != 0) {
+        set_error("ncclAllGather: %s", n->GetErrorString ? n->GetErrorString(rc) : "error");
+        return PF_ERR_NCCL;
+    }
+    std::vector<double> all(2 * (size_t) per * G);
+    PF_CUDA(cudaMemcpyAsync(all.data(), e.d_ns_recv, all.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+    PF_CUDA(cudaStreamSynchronize(e.stream));
+    for (uint32_t b = 0; b < B; ++b) {
+        const uint32_t r = b / per, i = b % per;
+        sum[b] = all[(size_t) r * 2 * per + i];
+        sum_sq[b] = all[(size_t) r * 2 * per + per + i];
+    }
+    return PF_OK;
+}
+
+static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                      const uint64_t* order, double* sum, double* sum_sq) {
+    if (e.node_split && e.nranks > 1 && !order) return eval_host_node_split(e, B, thetas, first_item, n_items, sum, sum_sq);
     PF_CUDA(cudaSetDevice(e.device));
     volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(e.h_out + 2 * kMaxNodesPerPass);
     for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
@@ -441,6 +500,7 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
     Engine& e = *reinterpret_cast<Engine*>(pe);
     switch (option) {
         case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
+        case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
     }
     pf::set_error("unknown option %d", option);
     return PF_ERR_INVALID;
@@ -503,6 +563,10 @@ int pf_eval_frontier_device(pf_engine* pe, uint32_t B, const double* d_thetas, d
     }
     if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e.stream;
+    if (e.node_split && e.nranks > 1) {
+        pf::set_error("node-split evaluation is available on the host-pointer path only");
+        return PF_ERR_UNSUPPORTED;
+    }
     if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !e.assume_identity;
     int r = pf::launch_model(e, B, d_thetas, d_out, 0, e.n_items, s);
     if (r != PF_OK) return r;
@@ -556,6 +620,9 @@ int pf_engine_comm_init(pf_engine* pe, const void* id128, int rank, int nranks) 
         return PF_ERR_NCCL;
     }
     e.nccl_comm = comm;
+    if (cudaMalloc(&e.d_ns_send, 2 * pf::kMaxNodesPerPass * 8) != cudaSuccess ||
+        cudaMalloc(&e.d_ns_recv, (size_t) nranks * 2 * pf::kMaxNodesPerPass * 8) != cudaSuccess)
+        return PF_ERR_NOMEM;
     return PF_OK;
 }
 

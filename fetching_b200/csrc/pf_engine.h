@@ -87,6 +87,9 @@ struct Engine {
 
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    bool node_split = false;      // PF_OPT_NODE_SPLIT: replicated data, nodes divided over ranks, all-gather
+    double* d_ns_send = nullptr;  // [2][per]
+    double* d_ns_recv = nullptr;  // [nranks][2][per]
     uint64_t launches = 0;
 };
 

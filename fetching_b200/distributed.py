@@ -24,6 +24,13 @@ def shard_rows(n_rows: int, item_rows: int, rank: int, world: int, n_items: int 
     return a * item_rows, b * item_rows
 
 
+def node_slices(n_nodes: int, world: int):
+    """Node-split mode (PF_OPT_NODE_SPLIT): rank r scores nodes [r*per, min((r+1)*per, B)), per = ceil(B/world);
+    trailing ranks may get none.  Mirrors eval_host_node_split() in csrc/pf_engine.cu."""
+    per = -(-n_nodes // world)
+    return [(min(r * per, n_nodes), min((r + 1) * per, n_nodes)) for r in range(world)]
+
+
 def init_engine_comm(engine, group=None) -> None:
     """Create the engine's NCCL communicator over the ranks of `group` (default: the world).
     The 128-byte NCCL id is made on rank 0 and broadcast through torch.distributed (any backend)."""

@@ -218,7 +218,11 @@ enum pf_option {
     /* PF_MODEL_NORMAL, device-pointer path only: promise that every node's covariance is the
      * identity (what the reference's proposals always produce, normalsampler.hh:73-75), which
      * selects the cheaper kernel.  The host-pointer path inspects the thetas itself. */
-    PF_OPT_ASSUME_IDENTITY_COV = 1
+    PF_OPT_ASSUME_IDENTITY_COV = 1,
+    /* After pf_engine_comm_init: 0 (default) = ROW SHARDS -- every rank holds different rows, per-node partial
+     * sums are all-reduced; 1 = NODE SPLIT -- every rank holds the WHOLE (small) data set, rank r scores nodes
+     * [r*ceil(B/G), ...) and the results are all-gathered (host-pointer calls only). */
+    PF_OPT_NODE_SPLIT = 2
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 

@@ -65,6 +65,25 @@ print("rank %d lasso   shard rows [%d,%d): rel err sum %.2e sum_sq %.2e" % (rank
 ok &= e1 < 1e-12 and e2 < 1e-12
 eng.close(); full.close()
 
+# node split (small data set replicated on every GPU; nodes divided over the ranks; all-gather)
+data, pos = models.mixture_dataset(100_000, 8, 2, seed=9)
+for B in (64, 13, 3):
+    thetas = models.mixture_thetas(pos, B, seed=B)
+    eng = fb.FrontierEngine.mixture(data, 8, 1000, device=local)
+    single = eng.eval_frontier(thetas)
+    pfd.init_engine_comm(eng)
+    eng.set_option(fb.OPT_NODE_SPLIT, 1)
+    s, q = eng.eval_frontier(thetas)
+    e1, e2 = rel(s, single[0]), rel(q, single[1])
+    if rank == 0:
+        print("node split B=%d over %d ranks: rel err sum %.2e sum_sq %.2e" % (B, world, e1, e2), flush=True)
+    ok &= e1 < 1e-12 and e2 < 1e-12
+    t = torch.from_numpy(np.stack([s, q])).cuda()
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    ok &= bool(torch.equal(t, t0))
+    eng.close()
+
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

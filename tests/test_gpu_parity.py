@@ -294,6 +294,37 @@ def test_boltzmann_dense(fb, orc, D, B):
     assert np.max(np.abs(q - s * s) / np.maximum(s * s, 1e-300)) < 1e-14
 
 
+def test_non_finite_inputs_propagate_like_the_reference(fb, orc):
+    """A NaN row poisons every node's sums (as numpy / the C++ loop would); an infinitely distant point gives
+    log(0) = -inf for the mixture and -inf for the normal target; finite nodes elsewhere are untouched."""
+    from fetching_b200 import models
+    data, pos = models.mixture_dataset(5000, 8, 2, seed=1)
+    th = models.mixture_thetas(pos, 3, seed=1)
+    bad = data.copy()
+    bad[1234, 1] = np.nan
+    with fb.FrontierEngine.mixture(bad, 8, 1000) as e:
+        s, q = e.eval_frontier(th)
+        s_ok, _ = e.eval_frontier_range(th, 2, 3)          # items 2..4 do not contain row 1234
+    assert np.all(np.isnan(s)) and np.all(np.isnan(q))
+    want = orc.mixture_frontier(data[2000:5000], th, 1000)
+    assert rel(s_ok, want[0]) < TOL64
+    far = data.copy()
+    far[77] = [np.inf, 0.0]
+    with fb.FrontierEngine.mixture(far, 8, 1000) as e:
+        s, _ = e.eval_frontier(th)
+    assert np.all(s == -np.inf) and orc.mixture_item(far, th[0], 1000, 0) == -np.inf
+    nd = orc.normal_dataset(4000)
+    nd[5, 0] = np.nan
+    with fb.FrontierEngine.normal(nd) as e:
+        s, q = e.eval_frontier(models.normal_thetas(2, seed=1))
+    assert np.all(np.isnan(s)) and np.all(np.isnan(q))
+    X, y, beta = models.blasso_dataset(3000, 10, seed=1)
+    X[100, 3] = np.nan
+    with fb.FrontierEngine.blasso(X, y, item_rows=1000) as e:
+        s, _ = e.eval_frontier(models.blasso_thetas(beta, 2, seed=1))
+    assert np.all(np.isnan(s))
+
+
 # ------------------------------------------------------------------------------------ boundary behaviour
 def test_device_pointer_path_matches_host_path(fb, orc):
     import torch

@@ -67,3 +67,14 @@ def test_shard_items_partition():
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
     assert shard_rows(100_000_000, 1000, 3, 8) == (37_500_000, 50_000_000)
+
+
+def test_node_slices_cover_every_node_once():
+    from fetching_b200.distributed import node_slices
+    for B in (1, 3, 13, 64, 65):
+        for w in (1, 2, 4, 8):
+            cuts = node_slices(B, w)
+            assert len(cuts) == w and cuts[0][0] == 0 and cuts[-1][1] == B
+            covered = [b for lo, hi in cuts for b in range(lo, hi)]
+            assert covered == list(range(B))
+            assert max(hi - lo for lo, hi in cuts) == -(-B // w)
