@@ -89,6 +89,7 @@ SYMBOLS = {
     "pf_debug_math": (C.c_int, [C.c_int, _dp, _dp, C.c_size_t, C.c_int]),
     "pf_debug_fp64_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_issue_probe": (C.c_int, [C.c_int, _dp]),
+    "pf_debug_rf_probe": (C.c_int, [C.c_int, _dp]),
 }
 
 _lib = None

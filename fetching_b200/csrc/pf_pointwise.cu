@@ -79,6 +79,7 @@ template <int D, typename T, bool GENERAL>
 struct NormalModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = true;
+    static constexpr bool HAS_REDO = false;
     static constexpr bool THETA_IN_SMEM = false;
     using CT = typename ComputeOf<T>::type;
     struct Node {
@@ -176,6 +177,7 @@ struct MixtureModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = false;
     static constexpr bool THETA_IN_SMEM = true;
+    static constexpr bool HAS_REDO = true;
     using CT = typename ComputeOf<T>::type;
     struct Node {
         const CT* th;
@@ -200,7 +202,7 @@ struct MixtureModel {
         }
         return (CT) log(lp);
     }
-    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+    static __device__ __forceinline__ CT mix_sum(const Node& nd, const CT (&x)[D]) {
         // exp chains kept in flight per lane (bounded by the registers the row operands need)
 #ifdef PF_MIX_G
         constexpr int GMAX = PF_MIX_G;
@@ -230,8 +232,21 @@ struct MixtureModel {
                 for (int g = 0; g + w < G; g += 2 * w) v[g] += v[g + w];
             lp += v[0];
         }
-        if (needs_slow_path(lp)) return slow(nd.th, x);  // every component ~40 sigma away, or non-finite input
-        return log_pos_fast(lp, nd.ltab);
+        return lp;
+    }
+    // Hot loop: branch free.  A row whose sum left the fast path's range (every component ~40 sigma away, or
+    // non-finite input) contributes 0 here and raises `redo`; the caller re-walks its rows of the tile with
+    // rowlp_redo afterwards, so the library call -- whose ABI clobbers the uniform registers holding the
+    // polynomial constants -- stays out of the loop the FP64 pipe lives in.
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], bool& redo) {
+        const CT lp = mix_sum(nd, x);
+        const bool bad = needs_slow_path(lp);
+        redo |= bad;
+        const CT v = log_pos_fast(lp, nd.ltab);
+        return bad ? (CT) 0 : v;
+    }
+    static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
+        return needs_slow_path(mix_sum(nd, x)) ? slow(nd.th, x) : (CT) 0;
     }
 };
 
@@ -242,6 +257,7 @@ struct MixtureModelRT {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = false;
     static constexpr bool THETA_IN_SMEM = true;
+    static constexpr bool HAS_REDO = true;
     using CT = typename ComputeOf<T>::type;
     struct Node {
         const CT* th;
@@ -255,7 +271,7 @@ struct MixtureModelRT {
         nd.ltab = ltab;
         nd.K = K;
     }
-    static __device__ __forceinline__ CT rowlp(const Node& nd, const CT (&x)[D]) {
+    static __device__ __forceinline__ CT mix_sum(const Node& nd, const CT (&x)[D]) {
         CT lp = 0;
         for (unsigned k = 0; k < nd.K; ++k) {
             CT e = 0;
@@ -266,19 +282,27 @@ struct MixtureModelRT {
             }
             lp += exp_neg_half_fast(e, nd.tab);
         }
-        if (needs_slow_path(lp)) {
-            double l2 = 0;
-            for (unsigned k = 0; k < nd.K; ++k) {
-                double e = 0;
-                for (int j = 0; j < D; ++j) {
-                    const double t = (double) nd.th[k * D + j] - (double) x[j];
-                    e = fma(t, t, e);
-                }
-                l2 += exp(-0.5 * e);
+        return lp;
+    }
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], bool& redo) {
+        const CT lp = mix_sum(nd, x);
+        const bool bad = needs_slow_path(lp);
+        redo |= bad;
+        const CT v = log_pos_fast(lp, nd.ltab);
+        return bad ? (CT) 0 : v;
+    }
+    static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
+        if (!needs_slow_path(mix_sum(nd, x))) return (CT) 0;
+        double l2 = 0;
+        for (unsigned k = 0; k < nd.K; ++k) {
+            double e = 0;
+            for (int j = 0; j < D; ++j) {
+                const double t = (double) nd.th[k * D + j] - (double) x[j];
+                e = fma(t, t, e);
             }
-            return (CT) log(l2);
+            l2 += exp(-0.5 * e);
         }
-        return log_pos_fast(lp, nd.ltab);
+        return (CT) log(l2);
     }
 };
 
@@ -461,14 +485,29 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                     }
             }
         }
+        [[maybe_unused]] bool redo = false;
         for (; j < nrows; j += nslots) {
             CT x[DIM];
             load_row<T, DIM, CT>(base + (size_t) j * RB_BYTES, x);
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
-                const double v = (double) M::rowlp(nd[n], x);
+                double v;
+                if constexpr (M::HAS_REDO)
+                    v = (double) M::rowlp_fast(nd[n], x, redo);
+                else
+                    v = (double) M::rowlp(nd[n], x);
                 accS[n] += v;
                 if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
+            }
+        }
+        if constexpr (M::HAS_REDO) {
+            if (redo) {  // cold: this lane's rows of the tile again, adding only the rows the fast path zeroed
+                for (unsigned j2 = slot; j2 < nrows; j2 += nslots) {
+                    CT x[DIM];
+                    load_row<T, DIM, CT>(base + (size_t) j2 * RB_BYTES, x);
+#pragma unroll
+                    for (int n = 0; n < NPL; ++n) accS[n] += (double) M::rowlp_redo(nd[n], x);
+                }
             }
         }
         if constexpr (M::ITEM1) {

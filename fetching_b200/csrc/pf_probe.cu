@@ -57,6 +57,97 @@ __global__ void fp64_mix_probe_kernel(double* out, int iters, double a, double b
     if (s == 12345.678 || t == 123456789) out[0] = s + t;
 }
 
+// DFMA with 1, 2 or 3 DISTINCT register operands (the rest loop-invariant / uniform): register-file bandwidth.
+//   NREG = 1:  x = fma(x, B, A)        (B, A uniform)
+//   NREG = 2:  x = fma(x, y, A)        (y a per-thread register)
+//   NREG = 3:  x = fma(y, w, x)        (the accumulate form of a dot product: three distinct register pairs)
+template <int NREG>
+__global__ void fp64_rf_probe_kernel(double* out, int iters, double a, double b) {
+    double x[8], y[8], w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = a + i + threadIdx.x * 1e-3;
+        y[i] = b - i * 1e-9 - threadIdx.x * 1e-12;
+        w[i] = 1e-9 * (i + 1) + threadIdx.x * 1e-13;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (NREG == 1) x[i] = fma(x[i], b, a);
+                else if (NREG == 2) x[i] = fma(x[i], y[i], a);
+                else x[i] = fma(y[i], w[(i + u) & 7], x[i]);
+            }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] + y[i] + w[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+// DFMA with two distinct register pairs + KINT cheap one-register integer ops per DFMA: does the second
+// register-file cycle of the DFMA block the dispatch of the integer op?
+template <int KINT>
+__global__ void fp64_rf_mix_probe_kernel(double* out, int iters, double a, double b) {
+    double x[8], y[8];
+    unsigned z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = a + i + threadIdx.x * 1e-3;
+        y[i] = 0.5 * b - i * 1e-9 - threadIdx.x * 1e-12;
+        z[i] = threadIdx.x * 7 + i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i] = fma(x[i], y[i], 1.5);  // immediate addend: exactly two register pairs
+#pragma unroll
+                for (int k = 0; k < KINT; ++k) z[i] = (z[i] ^ (0x9e3779b9u + 16 * u + k)) + 0x7f4a7c15u;  // LOP3 + IADD
+            }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] + y[i] + (double) z[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int KINT>
+static float run_rf_mix_probe(int sms, int iters, double* d_out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_rf_mix_probe_kernel<KINT><<<sms * 2, 256>>>(d_out, 16, 1.0000001, 0.9999999);
+    cudaEventRecord(e0);
+    fp64_rf_mix_probe_kernel<KINT><<<sms * 2, 256>>>(d_out, iters, 1.0000001, 0.9999999);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
+template <int NREG>
+static float run_rf_probe(int sms, int iters, double* d_out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_rf_probe_kernel<NREG><<<sms * 2, 256>>>(d_out, 16, 1.0000001, 0.9999999);
+    cudaEventRecord(e0);
+    fp64_rf_probe_kernel<NREG><<<sms * 2, 256>>>(d_out, iters, 1.0000001, 0.9999999);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
 template <int KINT>
 static float run_mix_probe(int sms, int iters, double* d_out) {
     cudaEvent_t e0, e1;
@@ -132,6 +223,24 @@ extern "C" PF_API int pf_debug_issue_probe(int device, double* out4) {
     const float ms[4] = {pf::run_mix_probe<0>(sms, iters, d_out), pf::run_mix_probe<1>(sms, iters, d_out),
                          pf::run_mix_probe<2>(sms, iters, d_out), pf::run_mix_probe<3>(sms, iters, d_out)};
     for (int k = 0; k < 4; ++k) out4[k] = (double) sms * 2 * 256 * iters * 16.0 * 8 / (ms[k] * 1e-3) / 1e12;
+    cudaFree(d_out);
+    return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+}
+
+// out3[n-1] = DFMA rate (1e12/s) at 16 warps/SM, 8 chains, with n = 1..3 distinct register operands per DFMA
+extern "C" PF_API int pf_debug_rf_probe(int device, double* out3) {
+    if (!out3 || cudaSetDevice(device) != cudaSuccess) return PF_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PF_ERR_CUDA;
+    const int sms = prop.multiProcessorCount, iters = 1024;
+    double* d_out = nullptr;
+    if (cudaMalloc(&d_out, 64) != cudaSuccess) return PF_ERR_NOMEM;
+    const float ms[3] = {pf::run_rf_probe<1>(sms, iters, d_out), pf::run_rf_probe<2>(sms, iters, d_out),
+                         pf::run_rf_probe<3>(sms, iters, d_out)};
+    for (int k = 0; k < 3; ++k) out3[k] = (double) sms * 2 * 256 * iters * 16.0 * 8 / (ms[k] * 1e-3) / 1e12;
+    // out3[3], out3[4]: two-register DFMA with 1 resp. 2 single-register ALU ops (2 resp. 4 instructions) between
+    const float mm[2] = {pf::run_rf_mix_probe<1>(sms, iters, d_out), pf::run_rf_mix_probe<2>(sms, iters, d_out)};
+    for (int k = 0; k < 2; ++k) out3[3 + k] = (double) sms * 2 * 256 * iters * 16.0 * 8 / (mm[k] * 1e-3) / 1e12;
     cudaFree(d_out);
     return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
 }

@@ -240,6 +240,9 @@ PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int
 PF_API int pf_debug_fp64_probe(int device, double* out16);
 /* Diagnostics: DFMA rate (1e12/s) with k = 0..3 integer multiply-adds interleaved per DFMA (issue-slot model). */
 PF_API int pf_debug_issue_probe(int device, double* out4);
+/* Diagnostics: DFMA rate (1e12/s) with 1, 2, 3 distinct register operands per DFMA, then a
+ * 2-register DFMA with 2 and 4 one-register ALU instructions between (register-file bandwidth); 5 values. */
+PF_API int pf_debug_rf_probe(int device, double* out5);
 
 #ifdef __cplusplus
 }

@@ -12,3 +12,8 @@ print("FMA/clk/SM:"); print(np.round(out.reshape(4,4) * 1e12 / clk / sms, 2))
 out4 = np.zeros(4)
 _lib.check(lib.pf_debug_issue_probe(0, out4.ctypes.data_as(C.POINTER(C.c_double))), "issue probe")
 print("DFMA/clk/SM with k integer IMADs interleaved per DFMA (k=0..3):", np.round(out4 * 1e12 / clk / sms, 2))
+
+out3 = np.zeros(5)
+_lib.check(lib.pf_debug_rf_probe(0, out3.ctypes.data_as(C.POINTER(C.c_double))), "rf probe")
+print("DFMA/clk/SM with 1, 2, 3 distinct register operands:", np.round(out3[:3] * 1e12 / clk / sms, 2))
+print("2-register DFMA + 2 / 4 one-register ALU instructions each:", np.round(out3[3:] * 1e12 / clk / sms, 2))
