@@ -181,12 +181,12 @@ struct MixtureModel {
     using CT = typename ComputeOf<T>::type;
     struct Node {
         const CT* th;
-        const double* tab;    // 2^(j/256) in shared memory
+        unsigned tab_s;       // 2^(j/256): shared-memory ADDRESS of the table, 2 KB aligned
         const double2* ltab;  // {1/c_j, log c_j} in shared memory
     };
     static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab, const double2* ltab) {
         nd.th = th_smem;
-        nd.tab = tab;
+        nd.tab_s = smem_u32(tab);
         nd.ltab = ltab;
     }
     // library exp/log: subnormal terms, log(0) = -inf, nan propagation exactly like numpy's
@@ -225,7 +225,7 @@ struct MixtureModel {
                     e[g] = fma(t, t, e[g]);
                 }
             }
-            exp_neg_half_fast_batch<G>(e, v, nd.tab);
+            exp_neg_half_fast_batch_s<G>(e, v, nd.tab_s);
 #pragma unroll
             for (int w = 1; w < G; w *= 2)  // pairwise: depth log2(G) instead of G dependent adds
 #pragma unroll
@@ -425,8 +425,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 
     typename M::Node nd[NPL];
     if constexpr (M::THETA_IN_SMEM) {
-        __shared__ __align__(16) double exp2_tab[kExp2TabSize];
+        // The 2^(j/256) table sits at a shared-memory ADDRESS aligned to its own size (exp_neg_half_fast_batch_s ORs
+        // the entry offset into it).  __align__ only aligns the offset behind the 1 KB the hardware reserves at
+        // the start of the window, so the aligned 2 KB are picked out of a 4 KB array by hand.
+        __shared__ __align__(16) double exp2_raw[2 * kExp2TabSize];
         __shared__ __align__(16) double2 log_tab[256];
+        constexpr unsigned kTabBytes = kExp2TabSize * 8;
+        const unsigned raw_s = smem_u32(exp2_raw);
+        double* const exp2_tab = exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
         for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
         for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
