@@ -284,6 +284,9 @@ def main():
     ap.add_argument("--frontier", type=int, default=8, help="frontier nodes per step (B)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only)")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: reduce the per-node partials inside the frontier kernel over NVLink peer memory "
+                         "(default) or with ncclAllReduce after it")
     ap.add_argument("--chain-length", type=int, default=50, help="levels of the chain-steps/s measurement")
     args = ap.parse_args()
 
@@ -298,7 +301,9 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     config = {"workload": args.workload + ": " + desc, "frontier_nodes": B, "rows_total": prm.get("rows", prm.get("D")),
-              "parallelism": "row-shard x%d + NCCL all-reduce of 2*B doubles" % world if world > 1 else "single GPU",
+              "parallelism": ("row-shard x%d + %s of 2*B doubles" % (
+                  world, "in-kernel NVLink peer exchange" if args.reduce == "peer" else "NCCL all-reduce"))
+              if world > 1 else "single GPU",
               "l2": "per-GPU input larger than L2 (no flush needed)" if kind in ("mixture", "blasso") and
               prm.get("rows", 0) * (16 if kind == "mixture" else 8 * prm.get("p", 1)) / world > 126e6
               else "input fits L2: steady-state L2-resident re-reads, as in a running chain"}
@@ -338,6 +343,9 @@ def main():
         ids = [fb.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         eng.comm_init(ids[0], rank, world)
+        if args.reduce == "peer":
+            from fetching_b200 import distributed as pfd
+            pfd.init_engine_peers(eng)
     shard.pop("data")  # the engine owns the device copy; free the host rows
 
     # an explicit stream: handle 0 (the legacy default stream) means "the engine's own stream" in the C ABI

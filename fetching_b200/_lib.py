@@ -19,6 +19,7 @@ MODEL_NORMAL, MODEL_BOLTZMANN_SCALAR, MODEL_BOLTZMANN_DENSE, MODEL_MIXTURE, MODE
 F64, F32 = 0, 1
 OPT_ASSUME_IDENTITY_COV = 1
 OPT_NODE_SPLIT = 2
+OPT_PEER_EXCHANGE = 3
 
 
 class ModelDesc(C.Structure):
@@ -81,6 +82,10 @@ SYMBOLS = {
     "pf_blasso_log_prior": (C.c_double, [_dp, C.c_uint32, C.c_double]),
     "pf_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pf_engine_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pf_engine_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pf_engine_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pf_engine_peer_attach_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "pf_engine_peer_status": (C.c_int, [C.c_void_p]),
     "pf_engine_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "pf_abi_version": (C.c_int, []),
     "pf_last_error": (C.c_char_p, []),

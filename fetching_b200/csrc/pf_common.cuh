@@ -217,4 +217,73 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
     Q_out = Q;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused all-reduce over NVLink peer memory (see PeerXchg in pf_engine.h).  Called by the consumer
+// threads of the finalizing CTA with this rank's totals in (S, Q) of threads tid < B; returns the
+// totals over all ranks, summed in rank order (identical bits on every rank).
+//   1. every rank stores its [S | Q] record into slot (seq & 1), row `rank`, of EVERY rank's buffer
+//      (plain peer stores, spread over the CTA), fences at system scope, then releases a flag = seq
+//      next to each record;
+//   2. it acquires the G flags of its OWN buffer and folds the G records.
+// Slot reuse is safe with two slots: a rank can only start call seq + 2 after it has seen every
+// peer's flag for seq + 1, which a peer publishes after it finished reading the records of seq.
+// A peer that never shows up (died, or made a different sequence of calls) trips a 20 s timeout:
+// *status = 1 in mapped host memory and the caller reports an error instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+static __device__ __noinline__ double2 peer_allreduce(const PeerXchg x, unsigned tid, unsigned B, unsigned nthreads,
+                                                      int bar_id, double* scratch, double S, double Q) {
+    const unsigned G = x.nranks;
+    const size_t slot_base = (size_t) (x.seq & 1) * kXchgMaxRanks * kXchgRec;
+    const size_t my_rec = slot_base + (size_t) x.rank * kXchgRec;
+    named_bar_sync(bar_id, (int) nthreads);  // everybody is done with `scratch`
+    if (tid < B) {
+        scratch[tid] = S;
+        scratch[kMaxNodesPerPass + tid] = Q;
+    }
+    named_bar_sync(bar_id, (int) nthreads);
+    for (unsigned i = tid; i < G * 2 * B; i += nthreads) {
+        const unsigned r = i / (2 * B), j = i - r * 2 * B;
+        const unsigned col = j < B ? j : kMaxNodesPerPass + (j - B);
+        x.peers[r][my_rec + col] = scratch[col];
+    }
+    __threadfence_system();
+    named_bar_sync(bar_id, (int) nthreads);
+    if (tid < G) {
+        unsigned long long* f = reinterpret_cast<unsigned long long*>(x.peers[tid] + my_rec + 2 * kMaxNodesPerPass);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(x.seq) : "memory");
+        // ... and wait for rank `tid`'s record in my own buffer
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(
+            x.peers[x.rank] + slot_base + (size_t) tid * kXchgRec + 2 * kMaxNodesPerPass);
+        const unsigned long long t0 = globaltimer_ns();
+        for (unsigned spins = 1;; ++spins) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (v == x.seq) break;
+            if ((spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) {
+                *reinterpret_cast<volatile unsigned int*>(x.status) = 1u;
+                __threadfence_system();
+                break;
+            }
+        }
+    }
+    named_bar_sync(bar_id, (int) nthreads);
+    if (tid < B) {
+        const double* mine = x.peers[x.rank] + slot_base;
+        double s = 0.0, q = 0.0;
+        for (unsigned r = 0; r < G; ++r) {
+            s += ld_cg_f64(mine + (size_t) r * kXchgRec + tid);
+            q += ld_cg_f64(mine + (size_t) r * kXchgRec + kMaxNodesPerPass + tid);
+        }
+        S = s;
+        Q = q;
+    }
+    return make_double2(S, Q);
+}
+
 }  // namespace pf

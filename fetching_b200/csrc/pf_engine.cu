@@ -76,7 +76,22 @@ static NcclApi* nccl_api() {
     return &api;
 }
 
+PeerXchg Engine::next_xchg() {
+    PeerXchg x{};
+    if (peer_fused && nranks > 1 && !node_split) {
+        x.peers = d_peers;
+        x.status = reinterpret_cast<unsigned int*>(d_hout + 2 * kMaxNodesPerPass + 1);
+        x.seq = ++xchg_seq;
+        x.rank = (unsigned) rank;
+        x.nranks = (unsigned) nranks;
+    }
+    return x;
+}
+
+static bool peer_active(const Engine& e) { return e.peer_fused && e.nranks > 1 && !e.node_split; }
+
 static int allreduce_out(Engine& e, double* d_out, uint32_t B, cudaStream_t s) {
+    if (peer_active(e)) return PF_OK;  // already reduced inside the frontier kernel (peer_allreduce)
     if (!e.nccl_comm || e.nranks <= 1 || e.node_split) return PF_OK;
     NcclApi* n = nccl_api();
     if (!n) {
@@ -143,6 +158,10 @@ static void destroy(Engine* e) {
     cudaFree(e->d_ns_send);
     cudaFree(e->d_ns_recv);
     cudaFree(e->d_ticket);
+    for (int r = 0; r < kXchgMaxRanks; ++r)
+        if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
+    cudaFree(e->d_xchg);
+    cudaFree(e->d_peers);
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -355,6 +374,16 @@ static int wait_flag(Engine& e, volatile unsigned long long* flag, unsigned long
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                      const uint64_t* order, double* sum, double* sum_sq);
 
+// the word after the completion flag in mapped host memory: set by peer_allreduce() on a timeout
+static int peer_status(Engine& e) {
+    volatile unsigned int* st = reinterpret_cast<unsigned int*>(e.h_out + 2 * kMaxNodesPerPass + 1);
+    if (*st) {
+        set_error("peer exchange timed out: a rank of the group did not reach this frontier call");
+        return PF_ERR_NCCL;
+    }
+    return PF_OK;
+}
+
 // Node-split (small data sets): the data set is replicated on every GPU, rank r scores nodes
 // [r*per, (r+1)*per) with the ordinary single-GPU kernel, and one ncclAllGather of 2*per doubles per rank hands
 // every rank every node's sums.  No data-path reduction: a node's sums come from exactly one GPU.
@@ -421,8 +450,8 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         // 56 vs 37 us per call for the normal target -- hundreds of small PCIe reads in front of the compute)
         PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
         // Fast path: one frontier kernel whose last CTA writes the 2*nb results into mapped host memory and then
-        // publishes a sequence number.  Not for NCCL-reduced results, ordered ranges, the scalar model or empty ranges.
-        const bool fast = !order && e.nranks <= 1 && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR && n_items > 0 &&
+        // publishes a sequence number.  Row-sharded groups reduce inside the same kernel (peer_allreduce).  Not for NCCL-reduced results, ordered ranges, the scalar model or empty ranges.
+        const bool fast = !order && (e.nranks <= 1 || peer_active(e)) && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR && n_items > 0 &&
                           first_item * e.item_rows < e.n_rows;
         int r;
         if (fast) {
@@ -433,6 +462,7 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
             if (r != PF_OK) return r;
             r = wait_flag(e, flag, e.done_seq);
             if (r != PF_OK) return r;
+            if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
             memcpy(sum + b0, e.h_out, (size_t) nb * 8);
             memcpy(sum_sq + b0, e.h_out + nb, (size_t) nb * 8);
             continue;
@@ -501,6 +531,17 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
     switch (option) {
         case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
         case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
+        case PF_OPT_PEER_EXCHANGE:
+            if (value != 0 && !e.peer_attached) {
+                pf::set_error("PF_OPT_PEER_EXCHANGE: no peer buffers attached (pf_engine_peer_attach)");
+                return PF_ERR_INVALID;
+            }
+            if (value == 0 && e.nranks > 1 && !e.nccl_comm) {
+                pf::set_error("PF_OPT_PEER_EXCHANGE = 0 needs the NCCL communicator (pf_engine_comm_init)");
+                return PF_ERR_INVALID;
+            }
+            e.peer_fused = value != 0;
+            return PF_OK;
     }
     pf::set_error("unknown option %d", option);
     return PF_ERR_INVALID;
@@ -624,6 +665,113 @@ int pf_engine_comm_init(pf_engine* pe, const void* id128, int rank, int nranks) 
         cudaMalloc(&e.d_ns_recv, (size_t) nranks * 2 * pf::kMaxNodesPerPass * 8) != cudaSuccess)
         return PF_ERR_NOMEM;
     return PF_OK;
+}
+
+static int peer_alloc(Engine& e) {
+    if (e.d_xchg) return PF_OK;
+    if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
+    const size_t bytes = (size_t) pf::kXchgSlots * pf::kXchgMaxRanks * pf::kXchgRec * 8;
+    // a plain cudaMalloc allocation of its own: cudaIpcGetMemHandle exports whole allocations
+    if (cudaMalloc(&e.d_xchg, bytes) != cudaSuccess || cudaMemset(e.d_xchg, 0, bytes) != cudaSuccess ||
+        cudaMalloc(&e.d_peers, pf::kXchgMaxRanks * sizeof(double*)) != cudaSuccess) {
+        pf::set_error("peer exchange: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return PF_ERR_NOMEM;
+    }
+    return PF_OK;
+}
+
+static int peer_finish(Engine& e, double* const* table, int rank, int nranks) {
+    if (cudaMemcpy(e.d_peers, table, (size_t) nranks * sizeof(double*), cudaMemcpyHostToDevice) != cudaSuccess) {
+        pf::set_error("peer exchange: pointer table upload failed");
+        return PF_ERR_CUDA;
+    }
+    e.rank = rank;
+    e.nranks = nranks;
+    e.xchg_seq = 0;
+    e.peer_attached = true;
+    e.peer_fused = true;
+    return PF_OK;
+}
+
+int pf_engine_peer_export(pf_engine* pe, void* handle64) {
+    if (!pe || !handle64) return PF_ERR_INVALID;
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    int r = peer_alloc(e);
+    if (r != PF_OK) return r;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, e.d_xchg) != cudaSuccess) {
+        pf::set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(cudaGetLastError()));
+        return PF_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return PF_OK;
+}
+
+int pf_engine_peer_attach(pf_engine* pe, const void* handles, int rank, int nranks) {
+    if (!pe || !handles || nranks < 1 || nranks > pf::kXchgMaxRanks || rank < 0 || rank >= nranks) {
+        pf::set_error("pf_engine_peer_attach: 1 <= nranks <= %d, 0 <= rank < nranks", pf::kXchgMaxRanks);
+        return PF_ERR_INVALID;
+    }
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    int r = peer_alloc(e);
+    if (r != PF_OK) return r;
+    if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
+    double* table[pf::kXchgMaxRanks] = {};
+    for (int k = 0; k < nranks; ++k) {
+        if (k == rank) {
+            table[k] = e.d_xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t) k * 64, 64);
+        void* p = nullptr;
+        // maps the peer's allocation into this process and enables peer access to its device
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {
+            pf::set_error("cudaIpcOpenMemHandle(rank %d): %s", k, cudaGetErrorString(ce));
+            cudaGetLastError();
+            return PF_ERR_CUDA;
+        }
+        e.peer_mapped[k] = p;
+        table[k] = static_cast<double*>(p);
+    }
+    return peer_finish(e, table, rank, nranks);
+}
+
+int pf_engine_peer_attach_local(pf_engine* const* engines, int nranks) {
+    if (!engines || nranks < 1 || nranks > pf::kXchgMaxRanks) return PF_ERR_INVALID;
+    double* table[pf::kXchgMaxRanks] = {};
+    for (int k = 0; k < nranks; ++k) {
+        if (!engines[k]) return PF_ERR_INVALID;
+        Engine& e = *reinterpret_cast<Engine*>(engines[k]);
+        int r = peer_alloc(e);
+        if (r != PF_OK) return r;
+        table[k] = e.d_xchg;
+    }
+    for (int k = 0; k < nranks; ++k) {
+        Engine& e = *reinterpret_cast<Engine*>(engines[k]);
+        if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
+        for (int j = 0; j < nranks; ++j) {
+            const int dj = reinterpret_cast<Engine*>(engines[j])->device;
+            if (dj == e.device) continue;
+            cudaError_t ce = cudaDeviceEnablePeerAccess(dj, 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) {
+                pf::set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", e.device, dj, cudaGetErrorString(ce));
+                cudaGetLastError();
+                return PF_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+        int r = peer_finish(e, table, k, nranks);
+        if (r != PF_OK) return r;
+    }
+    return PF_OK;
+}
+
+int pf_engine_peer_status(pf_engine* pe) {
+    if (!pe) return PF_ERR_INVALID;
+    return pf::peer_status(*reinterpret_cast<Engine*>(pe));
 }
 
 int pf_device_sm_count(int device) {

@@ -11,6 +11,21 @@ namespace pf {
 constexpr int kMaxNodesPerPass = 64;  // frontier nodes scored by one kernel launch
 constexpr int kPartSlots = 4;        // per-CTA record: S, Q, head, tail
 constexpr int kMaxGrid = 148 * 4;    // upper bound on CTAs per launch (sizes the partial buffer)
+constexpr int kXchgMaxRanks = 16;    // ranks in one peer-exchange group (one NVSwitch domain)
+constexpr int kXchgRec = 2 * kMaxNodesPerPass + 16;  // doubles per (slot, rank) record: S[64], Q[64], flag, pad
+constexpr int kXchgSlots = 2;        // records are double-buffered by call parity
+
+// In-kernel exchange of the per-node partials between the GPUs of a row-sharded engine group:
+// the finalizing CTA of every rank stores its [2][B] partials straight into every peer's exchange buffer
+// (NVLink / NVSwitch peer stores), publishes a sequence flag, waits for the other ranks' flags in its own
+// buffer and sums the records in rank order -- so every rank gets bit-identical totals and no collective
+// kernel, device->host copy or stream synchronisation follows the frontier kernel.  nranks <= 1: disabled.
+struct PeerXchg {
+    double* const* peers;      // device array [nranks]: base of every rank's exchange buffer (peer-mapped)
+    unsigned int* status;      // mapped host word, set to 1 when a peer did not show up in time
+    unsigned long long seq;    // call number, identical on every rank
+    unsigned int rank, nranks;
+};
 
 // Geometry of one launch of the pointwise (normal / mixture) kernels.
 struct PointwiseArgs {
@@ -27,6 +42,7 @@ struct PointwiseArgs {
     // results (system-scope fence), and the host polls the flag instead of copying + synchronising
     unsigned long long* done_flag;
     unsigned long long done_seq;
+    PeerXchg xchg;
 };
 
 // Geometry of one launch of the streamed-matrix (lasso / dense Boltzmann) kernel.
@@ -51,6 +67,7 @@ struct MatvecArgs {
     double inv_temperature;
     unsigned long long* done_flag;    // see PointwiseArgs
     unsigned long long done_seq;
+    PeerXchg xchg;
 };
 
 struct Engine {
@@ -90,6 +107,14 @@ struct Engine {
     bool node_split = false;      // PF_OPT_NODE_SPLIT: replicated data, nodes divided over ranks, all-gather
     double* d_ns_send = nullptr;  // [2][per]
     double* d_ns_recv = nullptr;  // [nranks][2][per]
+    // peer exchange (pf_engine_peer_export / _attach): fused all-reduce inside the frontier kernels
+    double* d_xchg = nullptr;              // my exchange buffer [kXchgSlots][kXchgMaxRanks][kXchgRec]
+    double** d_peers = nullptr;            // device table of every rank's buffer
+    void* peer_mapped[kXchgMaxRanks] = {}; // IPC mappings to close (nullptr for my own / same-process buffers)
+    bool peer_fused = false;               // the exchange is attached and selected (PF_OPT_PEER_EXCHANGE)
+    bool peer_attached = false;
+    unsigned long long xchg_seq = 0;
+    PeerXchg next_xchg();                  // arguments for the next launch (advances the call number)
     uint64_t launches = 0;
 };
 

@@ -317,6 +317,11 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
                        BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q);
+        if (a.xchg.nranks > 1) {
+            const double2 t = peer_allreduce(a.xchg, tid, B, MV_CONSUMERS, 1, red, S, Q);
+            S = t.x;
+            Q = t.y;
+        }
         if ((unsigned) tid < B) {
             if constexpr (BOLTZ) {
                 const double lp = -S * a.inv_temperature;  // one item: the whole energy
@@ -489,6 +494,7 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     a.inv_temperature = 1.0 / e.temperature;
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
+    a.xchg = e.next_xchg();
     if (a.row_end <= a.row_begin) {
         cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
         return 0;

@@ -594,6 +594,11 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
                        B, red, PW_BAR_ALL, PW_CONSUMERS, S, Q);
+        if (a.xchg.nranks > 1) {
+            const double2 t = peer_allreduce(a.xchg, tid, B, PW_CONSUMERS, PW_BAR_ALL, red, S, Q);
+            S = t.x;
+            Q = t.y;
+        }
         if ((unsigned) tid < B) {
             a.out[tid] = S;
             a.out[B + tid] = Q;
@@ -837,6 +842,7 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     a.K = e.K;
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
+    a.xchg = e.next_xchg();
     if (a.row_end <= a.row_begin) {
         cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
         return 0;

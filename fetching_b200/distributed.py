@@ -42,6 +42,17 @@ def init_engine_comm(engine, group=None) -> None:
     engine.comm_init(ids[0], rank, world)
 
 
+def init_engine_peers(engine, group=None) -> None:
+    """Attach the in-kernel peer exchange (pf_engine_peer_export / _attach): every rank's 64-byte CUDA IPC
+    handle is all-gathered through torch.distributed (any backend), then each engine maps its peers' buffers.
+    Afterwards the frontier kernels reduce the per-node partials themselves over NVLink peer memory."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.peer_export(), group=group)
+    engine.peer_attach(handles, rank, world)
+
+
 def combine_partials_host(sum_local, sum_sq_local, group=None):
     """Host-side equivalent of the engine's all-reduce (used by the gloo CPU tests of the sharding
     logic): partial (sum, sum_sq) per node are additive across item-aligned shards."""

@@ -125,6 +125,22 @@ class FrontierEngine:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         check(self._lib.pf_engine_comm_init(self._h, buf, rank, nranks), "pf_engine_comm_init")
 
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this engine's exchange buffer (pf_engine_peer_export)."""
+        buf = C.create_string_buffer(64)
+        check(self._lib.pf_engine_peer_export(self._h, buf), "pf_engine_peer_export")
+        return buf.raw
+
+    def peer_attach(self, handles, rank: int, nranks: int) -> None:
+        """`handles`: the 64-byte handles of all ranks in rank order; selects the in-kernel exchange."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self._lib.pf_engine_peer_attach(self._h, buf, rank, nranks), "pf_engine_peer_attach")
+
+    def peer_status(self) -> None:
+        check(self._lib.pf_engine_peer_status(self._h), "pf_engine_peer_status")
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.pf_engine_launch_count(self._h))
@@ -145,6 +161,12 @@ class FrontierEngine:
 
     def __exit__(self, *a):
         self.close()
+
+
+def peer_attach_local(engines) -> None:
+    """Attach the exchange buffers of engines that live in THIS process (rank = position in the list)."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    check(_lib.load().pf_engine_peer_attach_local(arr, len(engines)), "pf_engine_peer_attach_local")
 
 
 def nccl_unique_id() -> bytes:

@@ -148,6 +148,23 @@ PF_API double pf_blasso_log_prior(const double* theta, uint32_t p, double tau);
 PF_API int pf_nccl_unique_id(void* id128);
 PF_API int pf_engine_comm_init(pf_engine* e, const void* id128, int rank, int nranks);
 
+/* The same reduction WITHOUT a collective kernel: the frontier kernel's finalizing CTA stores this rank's
+ * [2][B] partials straight into every peer's exchange buffer over NVLink / NVSwitch (peer-mapped device
+ * memory), waits for the other ranks' records and sums them in rank order, so all ranks get bit-identical
+ * totals and the host path keeps its copy-free completion flag.  Replaces nothing in the reference (it has
+ * no data parallelism); replaces the ncclAllReduce above and is preferred once attached.
+ *   pf_engine_peer_export        64-byte CUDA IPC handle of this engine's exchange buffer (one process per GPU:
+ *                                all-gather the handles out of band, e.g. torch.distributed)
+ *   pf_engine_peer_attach        handles[nranks][64] of all ranks in rank order (own entry ignored); sets
+ *                                rank / nranks like pf_engine_comm_init and selects the fused exchange
+ *   pf_engine_peer_attach_local  all engines of the group live in THIS process (any devices): no IPC
+ *   pf_engine_peer_status        PF_ERR_NCCL after a call in which some rank never arrived (20 s timeout)
+ * Every rank must make the same sequence of evaluation calls (as with any collective). nranks <= 16. */
+PF_API int pf_engine_peer_export(pf_engine* e, void* handle64);
+PF_API int pf_engine_peer_attach(pf_engine* e, const void* handles, int rank, int nranks);
+PF_API int pf_engine_peer_attach_local(pf_engine* const* engines, int nranks);
+PF_API int pf_engine_peer_status(pf_engine* e);
+
 /* ---- a whole chain through the engine (host side: speculative tree + sampler + frontier hand-off) ----
  *
  * Equivalent of `mpirun -np frontier+1 ./fetching -S <sampler> -l chain_length -s policy -c correlation
@@ -222,7 +239,10 @@ enum pf_option {
     /* After pf_engine_comm_init: 0 (default) = ROW SHARDS -- every rank holds different rows, per-node partial
      * sums are all-reduced; 1 = NODE SPLIT -- every rank holds the WHOLE (small) data set, rank r scores nodes
      * [r*ceil(B/G), ...) and the results are all-gathered (host-pointer calls only). */
-    PF_OPT_NODE_SPLIT = 2
+    PF_OPT_NODE_SPLIT = 2,
+    /* Row shards: 1 = reduce inside the frontier kernel over peer memory (default once pf_engine_peer_attach
+     * succeeded), 0 = ncclAllReduce after the kernel (needs pf_engine_comm_init). */
+    PF_OPT_PEER_EXCHANGE = 3
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 

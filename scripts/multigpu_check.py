@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """torchrun --nproc-per-node N scripts/multigpu_check.py
 
-Row-sharded engines + the engine's NCCL all-reduce (pf_engine_comm_init) against a single engine
-holding the whole data set on rank 0's GPU, for the mixture and the lasso.  Prints one line per
+Row-sharded engines against a single engine holding the whole data set on the rank's GPU, for the
+mixture and the lasso, with both reductions: the in-kernel peer exchange over NVLink (CUDA IPC handles,
+pf_engine_peer_attach) and the NCCL all-reduce (pf_engine_comm_init).  Prints one line per
 check; exit code 0 only if every rank agrees to 1e-12 with the single-GPU totals."""
 import os
 import sys
@@ -33,6 +34,20 @@ lo, hi = pfd.shard_rows(len(data), 1000, rank, world)
 eng = fb.FrontierEngine.mixture(data[lo:hi], 8, 1000, device=local)
 pfd.init_engine_comm(eng)
 s, q = eng.eval_frontier(thetas)                      # host path: H2D, kernel, ncclAllReduce, D2H
+pfd.init_engine_peers(eng)                            # from here on: reduced inside the frontier kernel
+l0 = eng.launch_count
+for _ in range(5):
+    sp, qp = eng.eval_frontier(thetas)                # host path: H2D, ONE kernel, completion flag
+eng.peer_status()
+ok &= eng.launch_count - l0 == 5
+ok &= rel(sp, s) < 1e-13 and rel(qp, q) < 1e-13
+tp = torch.from_numpy(np.stack([sp, qp])).cuda()
+tp0 = tp.clone()
+dist.broadcast(tp0, src=0)
+ok &= bool(torch.equal(tp, tp0))                      # rank-order fold: identical bits on every rank
+print("rank %d mixture peer exchange vs NCCL: rel %.2e / %.2e, bit-identical across ranks %s" %
+      (rank, rel(sp, s), rel(qp, q), bool(torch.equal(tp, tp0))), flush=True)
+s, q = sp, qp
 d_th = torch.from_numpy(thetas).cuda()
 d_out = torch.zeros(2, 16, dtype=torch.float64, device="cuda")
 st = torch.cuda.Stream()
@@ -56,8 +71,9 @@ X, y, beta = models.blasso_dataset(20000, 96, seed=1)
 th = models.blasso_thetas(beta, 9, seed=1)
 lo, hi = pfd.shard_rows(20000, 500, rank, world)
 eng = fb.FrontierEngine.blasso(X[lo:hi], y[lo:hi], item_rows=500, device=local)
-pfd.init_engine_comm(eng)
+pfd.init_engine_peers(eng)                            # peer exchange only: no NCCL communicator at all
 s, q = eng.eval_frontier(th)
+eng.peer_status()
 full = fb.FrontierEngine.blasso(X, y, item_rows=500, device=local)
 fs, fq = full.eval_frontier(th)
 e1, e2 = rel(s, fs), rel(q, fq)
