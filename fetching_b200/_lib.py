@@ -20,6 +20,7 @@ F64, F32 = 0, 1
 OPT_ASSUME_IDENTITY_COV = 1
 OPT_NODE_SPLIT = 2
 OPT_PEER_EXCHANGE = 3
+OPT_MATVEC_TENSOR = 4
 
 
 class ModelDesc(C.Structure):
@@ -93,6 +94,7 @@ SYMBOLS = {
     "pf_device_sm_count": (C.c_int, [C.c_int]),
     "pf_debug_math": (C.c_int, [C.c_int, _dp, _dp, C.c_size_t, C.c_int]),
     "pf_debug_fp64_probe": (C.c_int, [C.c_int, _dp]),
+    "pf_debug_dmma_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_issue_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_rf_probe": (C.c_int, [C.c_int, _dp]),
 }

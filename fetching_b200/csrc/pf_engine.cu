@@ -531,6 +531,7 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
     switch (option) {
         case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
         case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
+        case PF_OPT_MATVEC_TENSOR: e.mv_tensor = value != 0; return PF_OK;
         case PF_OPT_PEER_EXCHANGE:
             if (value != 0 && !e.peer_attached) {
                 pf::set_error("PF_OPT_PEER_EXCHANGE: no peer buffers attached (pf_engine_peer_attach)");

@@ -18,8 +18,16 @@
 // RPL (coefficient) FP64 FMAs.  The epilogue (residual, square, scale / multiply by x_i) runs
 // in registers; item totals are assembled exactly like in pf_pointwise.cu.
 //
-// Arithmetic is FP64 FMA on the CUDA cores (the reference is IEEE double; sm_100a has no FP64
-// tcgen05 kind).  PF_F32 stores X/W and the panel as float and accumulates dots in float.
+// Arithmetic is IEEE double like the reference (sm_100a has no FP64 tcgen05 kind).  Two consumer variants:
+//   * vector (NBK = 0): FP64 FMA on the CUDA cores as described above -- used for frontiers of <= 8 nodes,
+//     where the kernel is HBM-bound, and for PF_F32 (X/W and the panel stored as float, float accumulation);
+//   * tensor (NBK = 2, 4, 8 blocks of 8 nodes): mma.sync.m8n8k4.f64 (SASS DMMA.884) -- the FP64 tensor-core
+//     instruction.  One DMMA is 256 FMAs from 4 register pairs, so the contraction is no longer limited by
+//     register-file bandwidth (the 3-operand DFMA form tops out at 43 of 64 FMA/clk/SM, scripts/fp64_probe.py,
+//     while DMMA issues at 63.8).  A warp owns 32 rows x all node blocks; A fragments come straight out of the
+//     swizzled TMA stage (conflict-free LDS.64), B fragments from a panel the prep kernel wrote in fragment
+//     order (lane-contiguous LDS.64).  Products and sums are exact IEEE FP64 FMAs, only the summation order
+//     over k differs from the vector variant.
 #include <math.h>
 #include <stdio.h>
 
@@ -52,6 +60,25 @@ __global__ void mv_prep_panel(const double* theta, T* panel, unsigned B, unsigne
     double v = 0.0;
     if (k < cols && b < B) v = theta[(size_t) b * theta_len + off + k];
     panel[idx] = (T) v;
+}
+
+// The same panel in DMMA fragment order: for 16-column chunk c, k-step s (4 columns), node block nb (8 nodes),
+// lane l holds B[k = l % 4][n = l / 4]:  panel[((c * 4 + s) * NBK + nb) * 32 + l] = theta[nb * 8 + l / 4][off + 16 c + 4 s + l % 4]
+__global__ void mv_prep_panel_frag(const double* theta, double* panel, unsigned B, unsigned NBK, unsigned theta_len,
+                                   unsigned off, unsigned cols, unsigned cols_pad) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cols_pad * NBK * 8) return;
+    const unsigned l = idx & 31, nb = (idx >> 5) % NBK, ks = (idx >> 5) / NBK;
+    const unsigned k = ks * 4 + (l & 3), b = nb * 8 + (l >> 2);
+    double v = 0.0;
+    if (k < cols && b < B) v = theta[(size_t) b * theta_len + off + k];
+    panel[idx] = v;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
 // Work units.  Lasso: the CTA's contiguous row range cut into tiles that never straddle an item,
@@ -96,9 +123,12 @@ struct UnitIter {
     }
 };
 
-template <typename T, int RPL, bool BOLTZ>
+template <typename T, int RPL, bool BOLTZ, int NBK>
 __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid_constant__ MatvecArgs a) {
     using CT = typename std::conditional<sizeof(T) == 4, float, double>::type;
+    constexpr bool MMA = NBK > 0;  // tensor variant: NBK blocks of 8 nodes per warp, 4 blocks of 8 rows per warp
+    constexpr int MB = 4;
+    static_assert(!MMA || sizeof(T) == 8, "DMMA is the FP64 path");
     constexpr int KPV = 16 / (int) sizeof(T);             // k values per 16-byte vector
     constexpr int KCH = MV_CHUNK_BYTES / (int) sizeof(T);  // k values per chunk
 
@@ -167,19 +197,30 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     const unsigned row_in_tile = rw * (32 * RPL) + lane;  // + 32*i
     const unsigned sw = lane & 7;                          // swizzle phase of all my rows
 
-    // per-node constants of the epilogue
-    double cst[MV_NODES_PER_LANE], hinv[MV_NODES_PER_LANE];
-#pragma unroll
-    for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
-        unsigned node = g * MV_NODES_PER_LANE + n;
-        if (node >= B) node = B - 1;
-        if constexpr (BOLTZ) {
-            cst[n] = 0.0;
-            hinv[n] = 0.0;
-        } else {
+    // per-node constants of the epilogue (tensor variant: in shared memory, a lane meets 2 * NBK nodes)
+    __shared__ double2 node_cst[MMA ? kMaxNodesPerPass : 1];  // {log(1/sigma/sqrt(2 pi)), 1/(2 sigma^2)}
+    [[maybe_unused]] double cst[MMA ? 1 : MV_NODES_PER_LANE], hinv[MMA ? 1 : MV_NODES_PER_LANE];
+    if constexpr (MMA) {
+        if (!BOLTZ && tid < kMaxNodesPerPass) {
+            const unsigned node = (unsigned) tid < B ? tid : B - 1;
             const double sigma = a.theta[(size_t) node * a.theta_len];
-            cst[n] = log(1 / sigma / sqrt(2 * 3.14159265358979323846));  // pyblasso.py:140
-            hinv[n] = 1.0 / (2.0 * sigma * sigma);
+            node_cst[tid] = make_double2(log(1 / sigma / sqrt(2 * 3.14159265358979323846)),  // pyblasso.py:140
+                                         1.0 / (2.0 * sigma * sigma));
+        }
+        named_bar_sync(1, MV_CONSUMERS);
+    } else {
+#pragma unroll
+        for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+            unsigned node = g * MV_NODES_PER_LANE + n;
+            if (node >= B) node = B - 1;
+            if constexpr (BOLTZ) {
+                cst[n] = 0.0;
+                hinv[n] = 0.0;
+            } else {
+                const double sigma = a.theta[(size_t) node * a.theta_len];
+                cst[n] = log(1 / sigma / sqrt(2 * 3.14159265358979323846));  // pyblasso.py:140
+                hinv[n] = 1.0 / (2.0 * sigma * sigma);
+            }
         }
     }
 
@@ -190,15 +231,50 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     unsigned long long t0, t1;
     unsigned c0, c1, q = 0, unit = 0;
     while (it.next(t0, t1, c0, c1)) {
-        CT acc[RPL][MV_NODES_PER_LANE];
+        CT acc[MMA ? 1 : RPL][MV_NODES_PER_LANE];
+        [[maybe_unused]] double cacc[MMA ? MB : 1][MMA ? NBK : 1][2];  // C fragments: row lane/4, nodes 2*(lane%4) + {0,1}
+        if constexpr (MMA) {
 #pragma unroll
-        for (int i = 0; i < RPL; ++i)
+            for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-            for (int n = 0; n < MV_NODES_PER_LANE; ++n) acc[i][n] = 0;
+                for (int nb = 0; nb < NBK; ++nb) cacc[mb][nb][0] = cacc[mb][nb][1] = 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int n = 0; n < MV_NODES_PER_LANE; ++n) acc[i][n] = 0;
+        }
 
         for (unsigned c = c0; c < c1; ++c, ++q) {
             const unsigned s = q % MV_STAGES;
             mbar_wait(&full[s], (q / MV_STAGES) & 1);
+            if constexpr (MMA) {
+                // A[row = lane/4][k = lane%4] of row block mb, k-step ks: 16-byte chunk (2 ks + (lane%4)/2) of the
+                // row, swizzled with row & 7 == lane / 4 (row blocks start at multiples of 8), half lane & 1
+                const unsigned char* xw = xstage + s * MV_XSTAGE_BYTES +
+                                          (size_t) (warp * (8 * MB) + (lane >> 2)) * MV_CHUNK_BYTES + ((lane & 1) << 3);
+                const unsigned c0x = (((lane >> 1) & 1) ^ (lane >> 2)) << 4;
+                const double* bw = reinterpret_cast<const double*>(bstage + s * MV_BSTAGE_BYTES) + lane;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    double bf[NBK];
+#pragma unroll
+                    for (int nb = 0; nb < NBK; ++nb) bf[nb] = bw[(ks * NBK + nb) * 32];
+                    // row blocks past the end of a short tile hold stale rows: they only feed their own (masked)
+                    // accumulator rows, and an unconditional instruction stream keeps every load ahead of its DMMAs
+                    double af[MB];
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+                        af[mb] = *reinterpret_cast<const double*>(xw + mb * 8 * MV_CHUNK_BYTES + (c0x ^ (unsigned) (ks << 5)));
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                        for (int nb = 0; nb < NBK; ++nb) dmma884(cacc[mb][nb][0], cacc[mb][nb][1], af[mb], bf[nb]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                continue;
+            }
             const unsigned char* xs = xstage + s * MV_XSTAGE_BYTES + (size_t) row_in_tile * MV_CHUNK_BYTES;
             const T* bs = reinterpret_cast<const T*>(bstage + s * MV_BSTAGE_BYTES) + g * MV_NODES_PER_LANE;
 #pragma unroll
@@ -234,11 +310,62 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
             if (ie < t1) ts = ie;
         }
         const bool split = ts < t1;
+        double* rbuf = red + (unit & 1) * (2 * MV_CONSUMER_WARPS * kMaxNodesPerPass);
+        if constexpr (MMA) {
+            // my rows: block mb, row lane/4; my nodes: block nb, 2*(lane%4) + {0,1}
+            double yv[MB];
+            bool live[MB], first[MB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const unsigned long long r = t0 + warp * (8 * MB) + mb * 8 + (lane >> 2);
+                live[mb] = r < t1;
+                first[mb] = r < ts;
+                yv[mb] = 0.0;
+                if constexpr (!BOLTZ)
+                    if (live[mb]) yv[mb] = __ldg(&a.y[r]);
+            }
+#pragma unroll
+            for (int nb = 0; nb < NBK; ++nb) {
+                const unsigned node0 = nb * 8 + 2 * (lane & 3);
+                double pA[2] = {0.0, 0.0}, pB[2] = {0.0, 0.0};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned node = node0 + h < B ? node0 + h : B - 1;
+                    [[maybe_unused]] double2 ch = make_double2(0.0, 0.0);
+                    if constexpr (!BOLTZ) ch = node_cst[node];
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        if (!live[mb]) continue;
+                        if constexpr (BOLTZ) {
+                            const unsigned long long r = t0 + warp * (8 * MB) + mb * 8 + (lane >> 2);
+                            const double xi = __ldg(&a.theta[(size_t) node * a.theta_len + r]);
+                            pA[h] = fma(xi, cacc[mb][nb][h], pA[h]);
+                        } else {
+                            const double res = cacc[mb][nb][h] - yv[mb];
+                            const double lp = ch.x - res * res * ch.y;
+                            pA[h] += first[mb] ? lp : 0.0;
+                            pB[h] += first[mb] ? 0.0 : lp;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    for (int m = 16; m >= 4; m >>= 1) {
+                        pA[h] += shfl_xor_f64(pA[h], m);
+                        pB[h] += shfl_xor_f64(pB[h], m);
+                    }
+                    if (lane < 4) {
+                        rbuf[warp * kMaxNodesPerPass + node0 + h] = pA[h];
+                        rbuf[(MV_CONSUMER_WARPS + warp) * kMaxNodesPerPass + node0 + h] = pB[h];
+                    }
+                }
+            }
+        }
         double partA[MV_NODES_PER_LANE], partB[MV_NODES_PER_LANE];
 #pragma unroll
         for (int n = 0; n < MV_NODES_PER_LANE; ++n) partA[n] = partB[n] = 0.0;
 #pragma unroll
-        for (int i = 0; i < RPL; ++i) {
+        for (int i = 0; i < (MMA ? 0 : RPL); ++i) {
             const unsigned long long r = t0 + row_in_tile + 32 * i;
             if (r < t1) {
                 if constexpr (BOLTZ) {
@@ -262,14 +389,15 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
                 }
             }
         }
-        double* rbuf = red + (unit & 1) * (2 * MV_CONSUMER_WARPS * kMaxNodesPerPass);
+        if constexpr (!MMA) {
 #pragma unroll
-        for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
-            double v = partA[n];
-            for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
-            if (lane == 0) rbuf[rw * kMaxNodesPerPass + g * MV_NODES_PER_LANE + n] = v;
+            for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
+                double v = partA[n];
+                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_f64(v, m);
+                if (lane == 0) rbuf[rw * kMaxNodesPerPass + g * MV_NODES_PER_LANE + n] = v;
+            }
         }
-        if (split) {
+        if (!MMA && split) {
 #pragma unroll
             for (int n = 0; n < MV_NODES_PER_LANE; ++n) {
                 double v = partB[n];
@@ -280,7 +408,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         }
         named_bar_sync(1, MV_CONSUMERS);
         if ((unsigned) tid < B) {
-            const unsigned RW = MV_CONSUMER_WARPS / NG;
+            const unsigned RW = MMA ? MV_CONSUMER_WARPS : MV_CONSUMER_WARPS / NG;
             double tot = 0.0;
             for (unsigned w = 0; w < RW; ++w) tot += rbuf[w * kMaxNodesPerPass + tid];
             if constexpr (BOLTZ)
@@ -395,9 +523,9 @@ int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
     return 0;
 }
 
-template <typename T, int RPL, bool BOLTZ>
+template <typename T, int RPL, bool BOLTZ, int NBK = 0>
 int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
-    auto kern = mv_frontier_kernel<T, RPL, BOLTZ>;
+    auto kern = mv_frontier_kernel<T, RPL, BOLTZ, NBK>;
     static bool configured_dev[64] = {};
     if (!configured_dev[e.device & 63]) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMvSmem);
@@ -466,6 +594,15 @@ int dispatch_rpl(Engine& e, MatvecArgs& a, unsigned rpl, cudaStream_t s) {
     }
 }
 
+template <bool BOLTZ>
+int dispatch_mma(Engine& e, MatvecArgs& a, unsigned nbk, cudaStream_t s) {
+    switch (nbk) {
+        case 2: return launch_mv<double, 1, BOLTZ, 2>(e, a, s);
+        case 4: return launch_mv<double, 1, BOLTZ, 4>(e, a, s);
+        default: return launch_mv<double, 1, BOLTZ, 8>(e, a, s);
+    }
+}
+
 }  // namespace
 
 int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
@@ -475,7 +612,8 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     unsigned NG = 1;
     while (NG * MV_NODES_PER_LANE < B) NG *= 2;  // 1, 2, 4, 8
     const unsigned rpl = NG == 1 ? 1 : (NG == 2 ? 2 : 4);
-    a.tile_rows = (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // 256, 256, 256, 128
+    const bool mma = !e.f32 && NG >= 2 && e.mv_tensor;  // FP64 tensor cores (DMMA) for frontiers of > 8 nodes
+    a.tile_rows = mma ? 256 : (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // 256, 256, 256, 128
     a.B = B;
     a.Bpad = NG * MV_NODES_PER_LANE;
     a.theta = d_theta;
@@ -501,7 +639,10 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     }
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
-    if (e.f32)
+    if (mma)
+        mv_prep_panel_frag<<<(total + 255) / 256, 256, 0, s>>>(d_theta, static_cast<double*>(e.d_betaT), B, NG, e.theta_len,
+                                                               off, e.dim, e.cols_pad);
+    else if (e.f32)
         mv_prep_panel<float><<<(total + 255) / 256, 256, 0, s>>>(d_theta, static_cast<float*>(e.d_betaT), B, a.Bpad,
                                                                  e.theta_len, off, e.dim, e.cols_pad);
     else
@@ -513,7 +654,9 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
         return -1;
     }
     int r;
-    if (boltz)
+    if (mma)
+        r = boltz ? dispatch_mma<true>(e, a, NG, s) : dispatch_mma<false>(e, a, NG, s);
+    else if (boltz)
         r = e.f32 ? dispatch_rpl<float, true>(e, a, rpl, s) : dispatch_rpl<double, true>(e, a, rpl, s);
     else
         r = e.f32 ? dispatch_rpl<float, false>(e, a, rpl, s) : dispatch_rpl<double, false>(e, a, rpl, s);

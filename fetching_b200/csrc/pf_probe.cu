@@ -114,6 +114,54 @@ __global__ void fp64_rf_mix_probe_kernel(double* out, int iters, double a, doubl
     if (s == 12345.678) out[0] = s;
 }
 
+// FP64 tensor-core probe: mma.sync.m8n8k4.f64 (SASS DMMA.884), ILP independent 8x8 accumulator tiles per warp.
+// One instruction = 8*8*4 = 256 FMAs per warp.  On B200 the FP64 tensor rate is specified equal to the vector
+// rate; this measures what the part actually issues (the B300 guide's "vestigial FP64" does not apply here).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int ILP>
+__global__ void dmma_probe_kernel(double* out, int iters, double a, double b) {
+    double c0[ILP], c1[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        c0[i] = a + i + threadIdx.x * 1e-3;
+        c1[i] = a - i;
+    }
+    const double av = a * 1e-3 + threadIdx.x * 1e-9, bv = b * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) dmma884(c0[i], c1[i], av, bv);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c0[i] + c1[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+static float run_dmma_probe(int sms, int warps_per_sm, int iters, double* d_out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int threads = 256, ctas_per_sm = warps_per_sm / 8;
+    dmma_probe_kernel<ILP><<<sms * ctas_per_sm, threads>>>(d_out, 16, 1.0000001, 0.9999999);
+    cudaEventRecord(e0);
+    dmma_probe_kernel<ILP><<<sms * ctas_per_sm, threads>>>(d_out, iters, 1.0000001, 0.9999999);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
 template <int KINT>
 static float run_rf_mix_probe(int sms, int iters, double* d_out) {
     cudaEvent_t e0, e1;
@@ -207,6 +255,26 @@ extern "C" PF_API int pf_debug_fp64_probe(int device, double* out16) {
             const double fmas = (double) sms * wlist[w] * 32.0 * iters * 16.0 * ilp[i];
             out16[4 * w + i] = fmas / (ms[i] * 1e-3) / 1e12;
         }
+    }
+    cudaFree(d_out);
+    return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+}
+
+// out8[4 * w + i] = FMA/s (1e12) through DMMA m8n8k4 for warps_per_sm = {8, 16}[w], ILP = {1,2,4,8}[i]
+extern "C" PF_API int pf_debug_dmma_probe(int device, double* out8) {
+    if (!out8 || cudaSetDevice(device) != cudaSuccess) return PF_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PF_ERR_CUDA;
+    const int sms = prop.multiProcessorCount, iters = 1024;
+    double* d_out = nullptr;
+    if (cudaMalloc(&d_out, 64) != cudaSuccess) return PF_ERR_NOMEM;
+    const int wlist[2] = {8, 16};
+    for (int w = 0; w < 2; ++w) {
+        const float ms[4] = {pf::run_dmma_probe<1>(sms, wlist[w], iters, d_out), pf::run_dmma_probe<2>(sms, wlist[w], iters, d_out),
+                             pf::run_dmma_probe<4>(sms, wlist[w], iters, d_out), pf::run_dmma_probe<8>(sms, wlist[w], iters, d_out)};
+        const int ilp[4] = {1, 2, 4, 8};
+        for (int i = 0; i < 4; ++i)
+            out8[4 * w + i] = (double) sms * wlist[w] * iters * 16.0 * ilp[i] * 256.0 / (ms[i] * 1e-3) / 1e12;
     }
     cudaFree(d_out);
     return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;

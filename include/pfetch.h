@@ -242,7 +242,11 @@ enum pf_option {
     PF_OPT_NODE_SPLIT = 2,
     /* Row shards: 1 = reduce inside the frontier kernel over peer memory (default once pf_engine_peer_attach
      * succeeded), 0 = ncclAllReduce after the kernel (needs pf_engine_comm_init). */
-    PF_OPT_PEER_EXCHANGE = 3
+    PF_OPT_PEER_EXCHANGE = 3,
+    /* Lasso / dense Boltzmann, FP64, frontiers of more than 8 nodes: 1 (default) = contraction on the FP64
+     * tensor cores (mma.sync.m8n8k4.f64, DMMA), 0 = FP64 FMA on the CUDA cores (the variant always used for
+     * <= 8 nodes and for PF_F32).  Same IEEE arithmetic, different summation order over the columns. */
+    PF_OPT_MATVEC_TENSOR = 4
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 
@@ -258,6 +262,9 @@ PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int
  * independent chains per thread in {1,2,4,8}; out16[4*w + i].  The largest entry is the FP64
  * roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
 PF_API int pf_debug_fp64_probe(int device, double* out16);
+/* Diagnostics: FMA rate (1e12/s) through the FP64 tensor-core instruction mma.sync.m8n8k4.f64 (DMMA) for
+ * warps/SM in {8,16} x independent accumulator tiles per warp in {1,2,4,8}; out8[4*w + i]. */
+PF_API int pf_debug_dmma_probe(int device, double* out8);
 /* Diagnostics: DFMA rate (1e12/s) with k = 0..3 integer multiply-adds interleaved per DFMA (issue-slot model). */
 PF_API int pf_debug_issue_probe(int device, double* out4);
 /* Diagnostics: DFMA rate (1e12/s) with 1, 2, 3 distinct register operands per DFMA, then a

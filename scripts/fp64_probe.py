@@ -17,3 +17,8 @@ out3 = np.zeros(5)
 _lib.check(lib.pf_debug_rf_probe(0, out3.ctypes.data_as(C.POINTER(C.c_double))), "rf probe")
 print("DFMA/clk/SM with 1, 2, 3 distinct register operands:", np.round(out3[:3] * 1e12 / clk / sms, 2))
 print("2-register DFMA + 2 / 4 one-register ALU instructions each:", np.round(out3[3:] * 1e12 / clk / sms, 2))
+
+out8 = np.zeros(8)
+_lib.check(lib.pf_debug_dmma_probe(0, out8.ctypes.data_as(C.POINTER(C.c_double))), "dmma probe")
+print("DMMA m8n8k4 FMA/clk/SM; rows: warps/SM 8,16; cols: accumulator tiles per warp 1,2,4,8:")
+print(np.round(out8.reshape(2, 4) * 1e12 / clk / sms, 2))

@@ -259,6 +259,27 @@ def test_blasso_shapes(fb, orc, n, p, item_rows):
     assert rel(s, want[0]) < TOL64 and rel(q, want[1]) < TOL64
 
 
+@pytest.mark.parametrize("n,p,item_rows,B", [(6000, 100, 500, 16), (5000, 37, 333, 9), (20000, 16, 18000, 64),
+                                              (777, 3, 100, 24), (4096, 1000, 1000, 40)])
+def test_blasso_tensor_variant_matches_vector_variant(fb, orc, n, p, item_rows, B):
+    """B > 8 runs the contraction on the FP64 tensor cores (DMMA m8n8k4); PF_OPT_MATVEC_TENSOR = 0 keeps the
+    CUDA-core FMA variant.  Both are exact IEEE FP64 FMAs, only the summation order over columns differs."""
+    from fetching_b200 import models
+    X, y, beta = models.blasso_dataset(n, p, seed=p)
+    th = models.blasso_thetas(beta, B, seed=B, scale=0.03)
+    want = orc.blasso_frontier(X, y, th, item_rows)
+    with fb.FrontierEngine.blasso(X, y, item_rows=item_rows) as e:
+        st, qt = e.eval_frontier(th)
+        first = 1 if e.data_size > 1 else 0
+        pt = e.eval_frontier_range(th, first, max(1, e.data_size // 2))  # a partial item range through the same path
+        e.set_option(fb.OPT_MATVEC_TENSOR, 0)
+        sv, qv = e.eval_frontier(th)
+        pv = e.eval_frontier_range(th, first, max(1, e.data_size // 2))
+    assert rel(st, want[0]) < TOL64 and rel(qt, want[1]) < TOL64
+    assert rel(st, sv) < 1e-12 and rel(qt, qv) < 1e-12
+    assert rel(pt[0], pv[0]) < 1e-12 and rel(pt[1], pv[1]) < 1e-12
+
+
 def test_blasso_f32_mode(fb, orc):
     from fetching_b200 import models
     X, y, beta = models.blasso_dataset(8000, 200, seed=3)
@@ -292,6 +313,11 @@ def test_boltzmann_dense(fb, orc, D, B):
     scale = np.array([np.abs(np.outer(x, x) * W).sum() / 2.0 for x in X])
     assert np.max(np.abs(s - want[0]) / scale) < TOL64
     assert np.max(np.abs(q - s * s) / np.maximum(s * s, 1e-300)) < 1e-14
+    if B > 8:  # tensor-core (DMMA) variant above, CUDA-core variant here
+        with fb.FrontierEngine.boltzmann_dense(W, temperature=2.0) as e:
+            e.set_option(fb.OPT_MATVEC_TENSOR, 0)
+            sv, _ = e.eval_frontier(X)
+        assert np.max(np.abs(s - sv) / scale) < 1e-13
 
 
 def test_non_finite_inputs_propagate_like_the_reference(fb, orc):
