@@ -178,7 +178,7 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
         const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
         if (n_cta < gmax) gmax = (unsigned) n_cta;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (unsigned c = worker < NW ? worker : gmax; c < gmax; c += NW) {
         const double* pr = part + (size_t) c * 4 * kMaxNodesPerPass + bb;
         S += ld_cg_f64(pr);

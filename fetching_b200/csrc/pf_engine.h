@@ -81,7 +81,7 @@ struct Engine {
     double temperature = 1.0;
     bool normal_general = true;  // per call: some node has a non-identity covariance (or unknown)
     bool assume_identity = false;  // PF_OPT_ASSUME_IDENTITY_COV
-    bool mv_tensor = true;         // PF_OPT_MATVEC_TENSOR: DMMA variant of the matvec kernel for B > 8 (FP64 only)
+    bool mv_tensor = true;         // PF_OPT_MATVEC_TENSOR: DMMA variant of the matvec kernel (FP64 only)
 
     void* d_data = nullptr;      // data set (T), padded
     double* d_resp = nullptr;    // lasso response (always double)

@@ -19,9 +19,9 @@
 // in registers; item totals are assembled exactly like in pf_pointwise.cu.
 //
 // Arithmetic is IEEE double like the reference (sm_100a has no FP64 tcgen05 kind).  Two consumer variants:
-//   * vector (NBK = 0): FP64 FMA on the CUDA cores as described above -- used for frontiers of <= 8 nodes,
-//     where the kernel is HBM-bound, and for PF_F32 (X/W and the panel stored as float, float accumulation);
-//   * tensor (NBK = 2, 4, 8 blocks of 8 nodes): mma.sync.m8n8k4.f64 (SASS DMMA.884) -- the FP64 tensor-core
+//   * vector (NBK = 0): FMA on the CUDA cores as described above -- PF_F32 (X/W and the panel stored as float,
+//     float accumulation) and, on request (PF_OPT_MATVEC_TENSOR = 0), FP64;
+//   * tensor (NBK = 1, 2, 4, 8 blocks of 8 nodes; the FP64 default): mma.sync.m8n8k4.f64 (SASS DMMA.884) -- the FP64 tensor-core
 //     instruction.  One DMMA is 256 FMAs from 4 register pairs, so the contraction is no longer limited by
 //     register-file bandwidth (the 3-operand DFMA form tops out at 43 of 64 FMA/clk/SM, scripts/fp64_probe.py,
 //     while DMMA issues at 63.8).  A warp owns 32 rows x all node blocks; A fragments come straight out of the
@@ -54,6 +54,7 @@ constexpr size_t kMvSmem = 1024 /* alignment slack */ + (size_t) MV_STAGES * (MV
 template <typename T>
 __global__ void mv_prep_panel(const double* theta, T* panel, unsigned B, unsigned Bpad, unsigned theta_len,
                               unsigned off, unsigned cols, unsigned cols_pad) {
+    asm volatile("griddepcontrol.launch_dependents;");  // the frontier kernel may start its prologue now
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cols_pad * Bpad) return;
     const unsigned k = idx / Bpad, b = idx % Bpad;
@@ -66,6 +67,7 @@ __global__ void mv_prep_panel(const double* theta, T* panel, unsigned B, unsigne
 // lane l holds B[k = l % 4][n = l / 4]:  panel[((c * 4 + s) * NBK + nb) * 32 + l] = theta[nb * 8 + l / 4][off + 16 c + 4 s + l % 4]
 __global__ void mv_prep_panel_frag(const double* theta, double* panel, unsigned B, unsigned NBK, unsigned theta_len,
                                    unsigned off, unsigned cols, unsigned cols_pad) {
+    asm volatile("griddepcontrol.launch_dependents;");
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cols_pad * NBK * 8) return;
     const unsigned l = idx & 31, nb = (idx >> 5) % NBK, ks = (idx >> 5) / NBK;
@@ -175,6 +177,9 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             prefetch_tensormap(&a.tmap);
+            // programmatic dependent launch: everything above overlapped the panel prep kernel; its output
+            // (a.betaT) is first touched below
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             UnitIter<BOLTZ> it = proto;
             unsigned long long t0, t1;
             unsigned c0, c1, q = 0;
@@ -545,9 +550,10 @@ int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
     if (BOLTZ) {
         // enough (row tile, column split) units to occupy every SM
         const unsigned long long tiles = (rows + a.tile_rows - 1) / a.tile_rows;
-        unsigned splits = 1;
-        while ((unsigned long long) tiles * splits < (unsigned long long) e.sm_count && splits < n_chunks) splits *= 2;
+        // one unit per CTA when the matrix is small (a second round would double the latency-bound run time)
+        unsigned splits = tiles < (unsigned long long) e.sm_count ? (unsigned) ((unsigned long long) e.sm_count / tiles) : 1;
         if (splits > n_chunks) splits = n_chunks;
+        if (splits < 1) splits = 1;
         a.chunks_per_split = (n_chunks + splits - 1) / splits;
         a.k_splits = (n_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
         a.n_units = (unsigned) tiles * a.k_splits;
@@ -576,8 +582,18 @@ int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
     }
     if (make_tmap(e, a.tile_rows, &a.tmap) != 0) return -1;
     if (grid < 1) grid = 1;
-    kern<<<grid, MV_THREADS, kMvSmem, s>>>(a);
-    cudaError_t err = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MV_THREADS);
+    cfg.dynamicSmemBytes = kMvSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // start under the tail of mv_prep_panel*
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a);
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) {
         set_error("matvec kernel launch: %s", cudaGetErrorString(err));
         return -1;
@@ -597,6 +613,7 @@ int dispatch_rpl(Engine& e, MatvecArgs& a, unsigned rpl, cudaStream_t s) {
 template <bool BOLTZ>
 int dispatch_mma(Engine& e, MatvecArgs& a, unsigned nbk, cudaStream_t s) {
     switch (nbk) {
+        case 1: return launch_mv<double, 1, BOLTZ, 1>(e, a, s);
         case 2: return launch_mv<double, 1, BOLTZ, 2>(e, a, s);
         case 4: return launch_mv<double, 1, BOLTZ, 4>(e, a, s);
         default: return launch_mv<double, 1, BOLTZ, 8>(e, a, s);
@@ -612,7 +629,7 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     unsigned NG = 1;
     while (NG * MV_NODES_PER_LANE < B) NG *= 2;  // 1, 2, 4, 8
     const unsigned rpl = NG == 1 ? 1 : (NG == 2 ? 2 : 4);
-    const bool mma = !e.f32 && NG >= 2 && e.mv_tensor;  // FP64 tensor cores (DMMA) for frontiers of > 8 nodes
+    const bool mma = !e.f32 && e.mv_tensor;  // FP64: the contraction runs on the tensor cores (DMMA)
     a.tile_rows = mma ? 256 : (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // 256, 256, 256, 128
     a.B = B;
     a.Bpad = NG * MV_NODES_PER_LANE;
@@ -639,6 +656,14 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     }
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
+    static bool prep_configured[64] = {};
+    if (!prep_configured[e.device & 63]) {
+        // same shared-memory carve-out as the frontier kernel, so the SMs are not reconfigured twice per call
+        cudaFuncSetAttribute(mv_prep_panel_frag, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(mv_prep_panel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(mv_prep_panel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        prep_configured[e.device & 63] = true;
+    }
     if (mma)
         mv_prep_panel_frag<<<(total + 255) / 256, 256, 0, s>>>(d_theta, static_cast<double*>(e.d_betaT), B, NG, e.theta_len,
                                                                off, e.dim, e.cols_pad);

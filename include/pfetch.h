@@ -243,9 +243,9 @@ enum pf_option {
     /* Row shards: 1 = reduce inside the frontier kernel over peer memory (default once pf_engine_peer_attach
      * succeeded), 0 = ncclAllReduce after the kernel (needs pf_engine_comm_init). */
     PF_OPT_PEER_EXCHANGE = 3,
-    /* Lasso / dense Boltzmann, FP64, frontiers of more than 8 nodes: 1 (default) = contraction on the FP64
-     * tensor cores (mma.sync.m8n8k4.f64, DMMA), 0 = FP64 FMA on the CUDA cores (the variant always used for
-     * <= 8 nodes and for PF_F32).  Same IEEE arithmetic, different summation order over the columns. */
+    /* Lasso / dense Boltzmann, FP64: 1 (default) = contraction on the FP64 tensor cores (mma.sync.m8n8k4.f64,
+     * DMMA), 0 = FP64 FMA on the CUDA cores (the variant PF_F32 always uses).  Same IEEE arithmetic,
+     * different summation order over the columns. */
     PF_OPT_MATVEC_TENSOR = 4
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);

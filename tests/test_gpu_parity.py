@@ -260,9 +260,10 @@ def test_blasso_shapes(fb, orc, n, p, item_rows):
 
 
 @pytest.mark.parametrize("n,p,item_rows,B", [(6000, 100, 500, 16), (5000, 37, 333, 9), (20000, 16, 18000, 64),
-                                              (777, 3, 100, 24), (4096, 1000, 1000, 40)])
+                                              (777, 3, 100, 24), (4096, 1000, 1000, 40), (6000, 100, 500, 3),
+                                              (10000, 250, 1000, 8)])
 def test_blasso_tensor_variant_matches_vector_variant(fb, orc, n, p, item_rows, B):
-    """B > 8 runs the contraction on the FP64 tensor cores (DMMA m8n8k4); PF_OPT_MATVEC_TENSOR = 0 keeps the
+    """FP64 runs the contraction on the FP64 tensor cores (DMMA m8n8k4); PF_OPT_MATVEC_TENSOR = 0 selects the
     CUDA-core FMA variant.  Both are exact IEEE FP64 FMAs, only the summation order over columns differs."""
     from fetching_b200 import models
     X, y, beta = models.blasso_dataset(n, p, seed=p)
@@ -313,7 +314,7 @@ def test_boltzmann_dense(fb, orc, D, B):
     scale = np.array([np.abs(np.outer(x, x) * W).sum() / 2.0 for x in X])
     assert np.max(np.abs(s - want[0]) / scale) < TOL64
     assert np.max(np.abs(q - s * s) / np.maximum(s * s, 1e-300)) < 1e-14
-    if B > 8:  # tensor-core (DMMA) variant above, CUDA-core variant here
+    if True:  # tensor-core (DMMA) variant above, CUDA-core variant here
         with fb.FrontierEngine.boltzmann_dense(W, temperature=2.0) as e:
             e.set_option(fb.OPT_MATVEC_TENSOR, 0)
             sv, _ = e.eval_frontier(X)
