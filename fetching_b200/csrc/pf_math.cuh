@@ -436,6 +436,89 @@ __device__ __forceinline__ void exp_neg_half_fast_batch_s(const double (&e)[G], 
         out[c] = __hiloint2double(__double2hiint(p) + (kk[c] << 20), __double2loint(p));
     }
 }
+// ---------------------------------------------------------------------------------------------
+// Mixture inner loop, second generation: sum_c exp(-e_c / 2) accumulated straight into two partial sums.
+// Every instruction counts here: the kernel is bound by dispatch (an FP64 instruction holds the port for two
+// cycles, anything else for one; scripts/fp64_probe.py), so the exp is cut to 7 FP64 + 4 other instructions:
+//   * a 2048-entry table 2^(j/2048) (16 KB of shared memory) leaves |g| <= 2^-12, where the degree-3 Taylor
+//     polynomial of 2^g is exact to 3.4e-17 relative;
+//   * the table stores each entry with (j << 9) already SUBTRACTED from its high word, so the exponent surgery
+//     is a single IMAD: hi' + Z * 512 == hi + ((Z >> 11) << 20) for Z = rint(2048 z) = 2048 k + j;
+//   * the result is never formed on its own: lp += (2^k tab_j) * P(g) is one FMA (P = 1 + g(...), 1 ulp);
+//   * the argument is clamped on the integer pipe BEFORE the rounding trick (one min on the high word of
+//     e >= 0, in place): Z can neither wrap (the 256-entry version wrapped for |theta - x| > 3400) nor leave
+//     the normal range.  A clamped term is ~2^-1021: a row that is NaN / inf / absurdly far in EVERY
+//     component therefore sums to < 2^-959 and is re-done exactly by the slow path (needs_slow_path()); a NaN
+//     in a single component of theta would be lost, so the kernel flags non-finite thetas when it stages them
+//     and poisons that node's sums itself (what numpy does: NaN term -> NaN row -> NaN item).
+// ---------------------------------------------------------------------------------------------
+constexpr int kExpBigBits = 11;
+constexpr int kExpBigSize = 1 << kExpBigBits;
+constexpr double kRintMagicBig = 3298534883328.0;  // 1.5 * 2^41: rint(2048 z) lands in the low word
+constexpr int kExpArgClampHi = 0x40962000;         // high word of 1416.0: -e/2 log2(e) >= -1021.5
+// B3 is rounded to 21 significant bits (immediate operand; its term is <= 8e-13, the rounding costs 4e-19)
+constexpr double kExpB1 = 0.6931471805599453, kExpB2 = 0.2402265069591007, kExpB3 = 0.0555041134357452392578125;  // 0x3FAC6B0900000000
+// filled once per device by the host (pf_pointwise.cu: ensure_exp_table): long-double 2^(j/2048), high word - (j << 9)
+__device__ double g_exp2_big[kExpBigSize];
+
+template <int G>
+__device__ __forceinline__ void mix_exp_accumulate(double (&e)[G], double& lp0, double& lp1, unsigned tab_s) {
+    double g[G], tjs[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        // clamp in place (one VIMNMX on the high word; e >= 0 or NaN)
+        e[c] = __hiloint2double(min(__double2hiint(e[c]), kExpArgClampHi), __double2loint(e[c]));
+        const double t = fma(e[c], kNegHalfLog2e, kRintMagicBig);
+        const int Z = __double2loint(t);
+        g[c] = fma(e[c], kNegHalfLog2e, -(t - kRintMagicBig));
+        unsigned idx, addr;
+        double tj;
+        // LOP3 + IMAD + LDS (left to itself the compiler shifts first: SHL + LOP3 + IADD)
+        asm("and.b32 %0, %1, %2;" : "=r"(idx) : "r"(Z), "n"(kExpBigSize - 1));
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(idx), "r"(tab_s));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));
+        tjs[c] = __hiloint2double(__double2hiint(tj) + Z * 512, __double2loint(tj));
+    }
+    double P[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) P[c] = fma(kExpB3, g[c], kExpB2);
+#pragma unroll
+    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExpB1);
+#pragma unroll
+    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], 1.0);
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        if (c & 1)
+            lp1 = fma(tjs[c], P[c], lp1);
+        else
+            lp0 = fma(tjs[c], P[c], lp0);
+    }
+}
+
+// log_pos_fast for the same loop, with as many constants as possible in IMMEDIATE form (a DFMA immediate is the
+// high word of a double whose low word is zero): 1/5 and 1/6 are rounded to 21 significant bits (their terms are
+// <= 2^-40 r), ln 2 is split as a 21-bit head (n * head exact) + a full-precision tail.  Fewer 64-bit literals in
+// the loop means fewer UMOV pairs with which ptxas re-materialises them every iteration.
+constexpr double kLn2Head = 0.693147182464599609375;              // 0x3FE62E4300000000
+constexpr double kLn2Tail = -1.904654299957767878541823e-09;       // ln 2 - kLn2Head
+constexpr double kLogC5 = 0.2000000476837158203125;               // 0x3FC9999A00000000 ~ 1/5
+constexpr double kLogC6 = -0.16666662693023681640625;             // 0xBFC5555500000000 ~ -1/6
+__device__ __forceinline__ double log_pos_fast_k(double x, const double2* tab) {
+    const int hi = __double2hiint(x);
+    const int j = (hi >> 12) & 255;
+    const int n = (hi >> 20) - 1023 + (j >= kLogTabFirstHalf ? 1 : 0);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(x));
+    const double2 t = tab[j];
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(kLogC6, r, kLogC5);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    const double l1p = fma(r * r, p, r);
+    const double nd = (double) n;
+    return fma(nd, kLn2Head, fma(nd, kLn2Tail, t.y + l1p));
+}
+
 template <int G>
 __device__ __forceinline__ void exp_neg_half_fast_batch_s(const float (&e)[G], float (&out)[G], unsigned) {
 #pragma unroll

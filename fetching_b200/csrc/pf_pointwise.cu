@@ -24,6 +24,8 @@
 // handed to the finalize step as head/tail partials and stitched there in CTA order.
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
+#include <type_traits>
 
 #include "pf_common.cuh"
 #include "pf_engine.h"
@@ -179,9 +181,10 @@ struct MixtureModel {
     static constexpr bool THETA_IN_SMEM = true;
     static constexpr bool HAS_REDO = true;
     using CT = typename ComputeOf<T>::type;
+    static constexpr bool BIG_EXP_TABLE = sizeof(CT) == 8;  // FP64: 2048-entry table + mix_exp_accumulate
     struct Node {
         const CT* th;
-        unsigned tab_s;       // 2^(j/256): shared-memory ADDRESS of the table, 2 KB aligned
+        unsigned tab_s;       // shared-memory ADDRESS of the exp table (FP64: 2048 adjusted entries; float: unused)
         const double2* ltab;  // {1/c_j, log c_j} in shared memory
     };
     static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab, const double2* ltab) {
@@ -210,6 +213,27 @@ struct MixtureModel {
         constexpr int GMAX = D <= 2 ? 8 : (D <= 4 ? 4 : 2);
 #endif
         constexpr int G = (K % GMAX == 0) ? GMAX : ((K % 2 == 0) ? 2 : 1);
+        if constexpr (BIG_EXP_TABLE) {
+            double lp0 = 0.0, lp1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < K; k0 += G) {
+                double e[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    double th[D];
+                    load_row<double, D, double>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), th);
+                    const double t0 = th[0] - x[0];
+                    e[g] = t0 * t0;
+#pragma unroll
+                    for (int j = 1; j < D; ++j) {
+                        const double t = th[j] - x[j];
+                        e[g] = fma(t, t, e[g]);
+                    }
+                }
+                mix_exp_accumulate<G>(e, lp0, lp1, nd.tab_s);
+            }
+            return (CT) (lp0 + lp1);
+        }
         CT lp = 0;
 #pragma unroll
         for (int k0 = 0; k0 < K; k0 += G) {
@@ -242,7 +266,11 @@ struct MixtureModel {
         const CT lp = mix_sum(nd, x);
         const bool bad = needs_slow_path(lp);
         redo |= bad;
-        const CT v = log_pos_fast(lp, nd.ltab);
+        CT v;
+        if constexpr (BIG_EXP_TABLE)
+            v = log_pos_fast_k(lp, nd.ltab);
+        else
+            v = log_pos_fast(lp, nd.ltab);
         return bad ? (CT) 0 : v;
     }
     static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
@@ -332,6 +360,13 @@ struct TileIter {
 // (registers are granted per pair of warps: 2 x 8 x 32 x 128 = 64K).  Models whose per-lane
 // state is large get the whole register file of one CTA instead.
 // per-item models rotate 4 tile buffers; one-row-per-item models reduce once at the end (2 x warps x nodes)
+template <class M, class = void>
+struct BigExpTable { static constexpr bool value = false; };
+template <class M>
+struct BigExpTable<M, std::enable_if_t<M::BIG_EXP_TABLE>> { static constexpr bool value = true; };
+template <class M>
+__host__ __device__ constexpr bool big_exp_table() { return BigExpTable<M>::value; }
+
 template <class M>
 __host__ __device__ constexpr int pw_red_doubles() {
     return (M::ITEM1 ? 2 : PW_RED_BUFS) * PW_CONSUMER_WARPS * kMaxNodesPerPass;
@@ -382,12 +417,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     unsigned long long r1 = r0 + a.rows_per_cta;
     if (r1 > a.row_end) r1 = a.row_end;
 
+    __shared__ unsigned long long theta_nan;  // bit b: node b has a NaN in its theta (see mix_exp_accumulate)
     if (tid == 0) {
         for (int s = 0; s < PW_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], PW_CONSUMER_WARPS);
         }
         fence_barrier_init();
+        theta_nan = 0ull;
     }
     __syncthreads();
 
@@ -428,17 +465,25 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         // The 2^(j/256) table sits at a shared-memory ADDRESS aligned to its own size (exp_neg_half_fast_batch_s ORs
         // the entry offset into it).  __align__ only aligns the offset behind the 1 KB the hardware reserves at
         // the start of the window, so the aligned 2 KB are picked out of a 4 KB array by hand.
-        __shared__ __align__(16) double exp2_raw[2 * kExp2TabSize];
+        constexpr bool BIG = big_exp_table<M>();
+        __shared__ __align__(16) double exp2_raw[BIG ? kExpBigSize : 2 * kExp2TabSize];
         __shared__ __align__(16) double2 log_tab[256];
         constexpr unsigned kTabBytes = kExp2TabSize * 8;
         const unsigned raw_s = smem_u32(exp2_raw);
-        double* const exp2_tab = exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
-        for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
+        double* const exp2_tab = BIG ? exp2_raw : exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
+        if constexpr (BIG) {
+            for (int i = tid; i < kExpBigSize; i += PW_CONSUMERS) exp2_tab[i] = g_exp2_big[i];
+        } else {
+            for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
+        }
         for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
         for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
-            th_smem[node * stride + j] = (CT) a.theta[i];
+            const double v = a.theta[i];
+            th_smem[node * stride + j] = (CT) v;
+            if constexpr (BIG)
+                if (v != v) atomicOr(&theta_nan, 1ull << node);
         }
         named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
 #pragma unroll
@@ -577,6 +622,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     } else if ((unsigned) tid < B)
         own.finish();
     if ((unsigned) tid < B) {
+        if constexpr (big_exp_table<M>())
+            if ((theta_nan >> tid) & 1ull) own.S = own.Q = __longlong_as_double(0x7FF8000000000000ll);
         own.store(rec, tid);
         __threadfence();
     }
@@ -726,8 +773,30 @@ size_t pw_smem_bytes(unsigned theta_len, unsigned max_nodes) {
     return base + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
 }
 
+// g_exp2_big on the engine's device: 2^(j/2048) rounded from long double, (j << 9) subtracted from the high word
+int ensure_exp_table(Engine& e) {
+    static bool done[64] = {};
+    if (done[e.device & 63]) return 0;
+    static double host_tab[kExpBigSize];
+    for (int j = 0; j < kExpBigSize; ++j) {
+        const double v = (double) exp2l((long double) j / kExpBigSize);
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        bits -= (unsigned long long) ((unsigned) j << 9) << 32;
+        memcpy(&host_tab[j], &bits, 8);
+    }
+    if (cudaMemcpyToSymbol(g_exp2_big, host_tab, sizeof host_tab) != cudaSuccess) {
+        set_error("upload of the exp table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    done[e.device & 63] = true;
+    return 0;
+}
+
 template <class M, typename T, int NPL>
 int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
+    if constexpr (big_exp_table<M>())
+        if (ensure_exp_table(e) != 0) return -1;
     void (*kern)(const PointwiseArgs);
     if constexpr (pw_two_ctas<M, NPL>())
         kern = pw_frontier_kernel2<M, T, NPL>;
