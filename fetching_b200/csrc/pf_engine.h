@@ -129,6 +129,7 @@ int launch_normal_ordered(Engine& e, uint32_t B, const double* d_theta, double* 
 int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,
                             cudaStream_t s);
 uint32_t pointwise_max_frontier(const Engine& e);
+int ensure_exp_table_for(Engine& e);  // uploads the mixture loop's exp table to e.device (once per device)
 bool pointwise_supported(const Engine& e);
 
 void set_error(const char* fmt, ...);

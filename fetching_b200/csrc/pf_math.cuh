@@ -440,7 +440,7 @@ __device__ __forceinline__ void exp_neg_half_fast_batch_s(const double (&e)[G], 
 // Mixture inner loop, second generation: sum_c exp(-e_c / 2) accumulated straight into two partial sums.
 // Every instruction counts here: the kernel is bound by dispatch (an FP64 instruction holds the port for two
 // cycles, anything else for one; scripts/fp64_probe.py), so the exp is cut to 7 FP64 + 4 other instructions:
-//   * a 2048-entry table 2^(j/2048) (16 KB of shared memory) leaves |g| <= 2^-12, where the degree-3 Taylor
+//   * a 2048-entry table B3 2^(j/2048) (16 KB of shared memory) leaves |g| <= 2^-12, where the degree-3 Taylor
 //     polynomial of 2^g is exact to 3.4e-17 relative;
 //   * the table stores each entry with (j << 9) already SUBTRACTED from its high word, so the exponent surgery
 //     is a single IMAD: hi' + Z * 512 == hi + ((Z >> 11) << 20) for Z = rint(2048 z) = 2048 k + j;
@@ -455,10 +455,12 @@ __device__ __forceinline__ void exp_neg_half_fast_batch_s(const double (&e)[G], 
 constexpr int kExpBigBits = 11;
 constexpr int kExpBigSize = 1 << kExpBigBits;
 constexpr double kRintMagicBig = 3298534883328.0;  // 1.5 * 2^41: rint(2048 z) lands in the low word
-constexpr int kExpArgClampHi = 0x40962000;         // high word of 1416.0: -e/2 log2(e) >= -1021.5
-// B3 is rounded to 21 significant bits (immediate operand; its term is <= 8e-13, the rounding costs 4e-19)
-constexpr double kExpB1 = 0.6931471805599453, kExpB2 = 0.2402265069591007, kExpB3 = 0.0555041134357452392578125;  // 0x3FAC6B0900000000
-// filled once per device by the host (pf_pointwise.cu: ensure_exp_table): long-double 2^(j/2048), high word - (j << 9)
+constexpr int kExpArgClampHi = 0x40960000;         // high word of 1408.0: -e/2 log2(e) >= -1015.7 (entries are >= 2^-5)
+// 2^g = B3 (g^3 + Q2 g^2 + Q1 g + Q0) on |g| <= 2^-12 (truncation 3.4e-17): the MONIC form has exactly one constant
+// per instruction (a DADD and two FMAs; an FMA with two constants needs one of them in a register pair, which
+// ptxas re-materialises with two MOVs per iteration), and the leading coefficient B3 = ln2^3/6 lives in the table.
+constexpr double kExpQ2 = 4.328085122666891, kExpQ1 = 12.488213886033646, kExpQ0 = 18.016684242941434;
+// filled once per device by the host (pf_pointwise.cu: ensure_exp_table): long-double B3 2^(j/2048), high word - (j << 9)
 __device__ double g_exp2_big[kExpBigSize];
 
 template <int G>
@@ -481,11 +483,11 @@ __device__ __forceinline__ void mix_exp_accumulate(double (&e)[G], double& lp0, 
     }
     double P[G];
 #pragma unroll
-    for (int c = 0; c < G; ++c) P[c] = fma(kExpB3, g[c], kExpB2);
+    for (int c = 0; c < G; ++c) P[c] = g[c] + kExpQ2;
 #pragma unroll
-    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExpB1);
+    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExpQ1);
 #pragma unroll
-    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], 1.0);
+    for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExpQ0);
 #pragma unroll
     for (int c = 0; c < G; ++c) {
         if (c & 1)
@@ -503,12 +505,16 @@ constexpr double kLn2Head = 0.693147182464599609375;              // 0x3FE62E430
 constexpr double kLn2Tail = -1.904654299957767878541823e-09;       // ln 2 - kLn2Head
 constexpr double kLogC5 = 0.2000000476837158203125;               // 0x3FC9999A00000000 ~ 1/5
 constexpr double kLogC6 = -0.16666662693023681640625;             // 0xBFC5555500000000 ~ -1/6
-__device__ __forceinline__ double log_pos_fast_k(double x, const double2* tab) {
+// The table handed to this version has 1/c_j DOUBLED for j >= kLogTabFirstHalf, because m = x 2^-n is formed with
+// the n that already includes the "+1" of the upper half (m in [0.707, 1.414)): adding 0x96000 to the high word
+// carries into the exponent exactly when the mantissa is >= 106/256, so n and m cost 4 integer instructions.
+__device__ __forceinline__ double log_pos_fast_k(double x, unsigned ltab_s) {
     const int hi = __double2hiint(x);
-    const int j = (hi >> 12) & 255;
-    const int n = (hi >> 20) - 1023 + (j >= kLogTabFirstHalf ? 1 : 0);
-    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(x));
-    const double2 t = tab[j];
+    const int A = hi + ((0x00100000 - (kLogTabFirstHalf << 12)) - 0x3FF00000);
+    const int n = A >> 20;
+    const double m = __hiloint2double(hi - (A & (int) 0xFFF00000), __double2loint(x));
+    double2 t;  // {1/c_j, log c_j}: the table is addressed by its 32-bit shared-memory address (no pointer to re-form)
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(ltab_s + ((unsigned) (hi >> 8) & 0xFF0u)));
     const double r = fma(m, t.x, -1.0);
     double p = fma(kLogC6, r, kLogC5);
     p = fma(p, r, -0.25);
@@ -541,6 +547,13 @@ __device__ __forceinline__ bool needs_slow_path(double lp) {
     return (unsigned) (__double2hiint(lp) - 0x04000000) >= 0x7BF00000u;
 }
 __device__ __forceinline__ bool needs_slow_path(float lp) { return !(lp >= 1e-30f && lp < 3e38f); }
+// The same test accumulated over many rows with one VIADD + one VIMNMX.U32 per row: acc = max(acc, key(lp)),
+// tested once per tile (acc_needs_slow_path).
+__device__ __forceinline__ void slow_path_accumulate(unsigned& acc, double lp) {
+    acc = max(acc, (unsigned) (__double2hiint(lp) - 0x04000000));
+}
+__device__ __forceinline__ void slow_path_accumulate(unsigned& acc, float lp) { acc |= needs_slow_path(lp) ? 0x80000000u : 0u; }
+__device__ __forceinline__ bool acc_needs_slow_path(unsigned acc) { return acc >= 0x7BF00000u; }
 
 // log(x) for x > 0 normal (callers route everything else through needs_slow_path / log()).
 // x = 2^n m; j = top 8 mantissa bits; r = m / c_j - 1 (one FMA, |r| <= 2^-8); log x = n ln2 + log c_j + log1p(r),

@@ -185,11 +185,13 @@ struct MixtureModel {
     struct Node {
         const CT* th;
         unsigned tab_s;       // shared-memory ADDRESS of the exp table (FP64: 2048 adjusted entries; float: unused)
+        unsigned ltab_s;      // ... and of the log table
         const double2* ltab;  // {1/c_j, log c_j} in shared memory
     };
     static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab, const double2* ltab) {
         nd.th = th_smem;
         nd.tab_s = smem_u32(tab);
+        nd.ltab_s = smem_u32(ltab);
         nd.ltab = ltab;
     }
     // library exp/log: subnormal terms, log(0) = -inf, nan propagation exactly like numpy's
@@ -259,22 +261,25 @@ struct MixtureModel {
         return lp;
     }
     // Hot loop: branch free.  A row whose sum left the fast path's range (every component ~40 sigma away, or
-    // non-finite input) contributes 0 here and raises `redo`; the caller re-walks its rows of the tile with
-    // rowlp_redo afterwards, so the library call -- whose ABI clobbers the uniform registers holding the
-    // polynomial constants -- stays out of the loop the FP64 pipe lives in.
-    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], bool& redo) {
+    // non-finite input) contributes garbage here and raises `redo`; the caller then DISCARDS this lane's sums of
+    // the tile and re-walks its rows with rowlp_redo (fast value, or the library for the rows out of range), so
+    // the library call -- whose ABI clobbers the uniform registers holding the polynomial constants -- and the
+    // masking selects stay out of the loop the FP64 pipe lives in.
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], unsigned& redo) {
         const CT lp = mix_sum(nd, x);
-        const bool bad = needs_slow_path(lp);
-        redo |= bad;
-        CT v;
+        slow_path_accumulate(redo, lp);  // the value is NOT masked (see above)
         if constexpr (BIG_EXP_TABLE)
-            v = log_pos_fast_k(lp, nd.ltab);
+            return log_pos_fast_k(lp, nd.ltab_s);
         else
-            v = log_pos_fast(lp, nd.ltab);
-        return bad ? (CT) 0 : v;
+            return log_pos_fast(lp, nd.ltab);
     }
     static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
-        return needs_slow_path(mix_sum(nd, x)) ? slow(nd.th, x) : (CT) 0;
+        const CT lp = mix_sum(nd, x);
+        if (needs_slow_path(lp)) return slow(nd.th, x);
+        if constexpr (BIG_EXP_TABLE)
+            return log_pos_fast_k(lp, nd.ltab_s);
+        else
+            return log_pos_fast(lp, nd.ltab);
     }
 };
 
@@ -312,15 +317,14 @@ struct MixtureModelRT {
         }
         return lp;
     }
-    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], bool& redo) {
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], unsigned& redo) {
         const CT lp = mix_sum(nd, x);
-        const bool bad = needs_slow_path(lp);
-        redo |= bad;
-        const CT v = log_pos_fast(lp, nd.ltab);
-        return bad ? (CT) 0 : v;
+        slow_path_accumulate(redo, lp);
+        return log_pos_fast(lp, nd.ltab);
     }
     static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
-        if (!needs_slow_path(mix_sum(nd, x))) return (CT) 0;
+        const CT lp = mix_sum(nd, x);
+        if (!needs_slow_path(lp)) return log_pos_fast(lp, nd.ltab);
         double l2 = 0;
         for (unsigned k = 0; k < nd.K; ++k) {
             double e = 0;
@@ -476,7 +480,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         } else {
             for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
         }
-        for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
+        for (int i = tid; i < 256; i += PW_CONSUMERS)  // log_pos_fast_k wants 1/c_j doubled in the upper half
+            log_tab[i] = make_double2(kLogTab[2 * i] * (BIG && i >= kLogTabFirstHalf ? 2.0 : 1.0), kLogTab[2 * i + 1]);
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
         for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
@@ -536,7 +541,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                     }
             }
         }
-        [[maybe_unused]] bool redo = false;
+        [[maybe_unused]] unsigned redo = 0u;  // slow_path_accumulate() key, tested once per tile
         for (; j < nrows; j += nslots) {
             CT x[DIM];
             load_row<T, DIM, CT>(base + (size_t) j * RB_BYTES, x);
@@ -552,7 +557,9 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             }
         }
         if constexpr (M::HAS_REDO) {
-            if (redo) {  // cold: this lane's rows of the tile again, adding only the rows the fast path zeroed
+            if (acc_needs_slow_path(redo)) {  // cold: discard this lane's sums of the tile (they start at 0 per tile) and walk its rows again
+#pragma unroll
+                for (int n = 0; n < NPL; ++n) accS[n] = 0.0;
                 for (unsigned j2 = slot; j2 < nrows; j2 += nslots) {
                     CT x[DIM];
                     load_row<T, DIM, CT>(base + (size_t) j2 * RB_BYTES, x);
@@ -759,6 +766,26 @@ __global__ void debug_math_kernel(int which, const double* in, double* out, size
     out[i] = r;
 }
 
+// diagnostics for the mixture loop's own pair (mix_exp_accumulate / log_pos_fast_k): which = 5: exp(-x/2), 6: log(x)
+__global__ void debug_math_kernel_big(int which, const double* in, double* out, size_t n) {
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    __shared__ double tab[kExpBigSize];
+    __shared__ __align__(16) double2 ltab[256];
+    for (int k = threadIdx.x; k < kExpBigSize; k += blockDim.x) tab[k] = g_exp2_big[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x)
+        ltab[k] = make_double2(kLogTab[2 * k] * (k >= kLogTabFirstHalf ? 2.0 : 1.0), kLogTab[2 * k + 1]);
+    __syncthreads();
+    if (i >= n) return;
+    double r;
+    if (which == 5) {
+        double e[1] = {in[i]}, lp0 = 0.0, lp1 = 0.0;
+        mix_exp_accumulate<1>(e, lp0, lp1, smem_u32(tab));
+        r = lp0 + lp1;
+    } else
+        r = log_pos_fast_k(in[i], smem_u32(ltab));
+    out[i] = r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: dispatch
 // ---------------------------------------------------------------------------------------------
@@ -773,13 +800,14 @@ size_t pw_smem_bytes(unsigned theta_len, unsigned max_nodes) {
     return base + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
 }
 
-// g_exp2_big on the engine's device: 2^(j/2048) rounded from long double, (j << 9) subtracted from the high word
+// g_exp2_big on the engine's device: B3 2^(j/2048) rounded from long double, (j << 9) subtracted from the high word
 int ensure_exp_table(Engine& e) {
     static bool done[64] = {};
     if (done[e.device & 63]) return 0;
     static double host_tab[kExpBigSize];
     for (int j = 0; j < kExpBigSize; ++j) {
-        const double v = (double) exp2l((long double) j / kExpBigSize);
+        const long double ln2 = 0.693147180559945309417232121458176568L;
+        const double v = (double) (ln2 * ln2 * ln2 / 6.0L * exp2l((long double) j / kExpBigSize));  // B3 2^(j/2048)
         unsigned long long bits;
         memcpy(&bits, &v, 8);
         bits -= (unsigned long long) ((unsigned) j << 9) << 32;
@@ -882,6 +910,9 @@ int dispatch_mixture(Engine& e, const PointwiseArgs& a, cudaStream_t s) {
 }
 
 }  // namespace
+
+int ensure_exp_table_for(Engine& e) { return ensure_exp_table(e); }
+
 
 bool pointwise_supported(const Engine& e) {
     const uint32_t d = e.dim;
@@ -994,7 +1025,13 @@ extern "C" PF_API int pf_debug_math(int which, const double* in, double* out, si
     double *d_in = nullptr, *d_out = nullptr;
     if (cudaMalloc(&d_in, n * 8) != cudaSuccess || cudaMalloc(&d_out, n * 8) != cudaSuccess) return PF_ERR_NOMEM;
     cudaMemcpy(d_in, in, n * 8, cudaMemcpyHostToDevice);
-    pf::debug_math_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(which, d_in, d_out, n);
+    if (which == 5 || which == 6) {
+        pf::Engine tmp;
+        tmp.device = device;
+        if (pf::ensure_exp_table_for(tmp) != 0) return PF_ERR_CUDA;
+        pf::debug_math_kernel_big<<<(unsigned) ((n + 255) / 256), 256>>>(which, d_in, d_out, n);
+    } else
+        pf::debug_math_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(which, d_in, d_out, n);
     cudaError_t err = cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_in);
     cudaFree(d_out);

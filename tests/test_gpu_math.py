@@ -70,3 +70,31 @@ def test_fp32_variants():
     assert (np.abs(got - want) / want).max() < 2e-5
     x = rng.uniform(1e-3, 8.0, 100000)
     assert np.abs(run(3, x) - np.log(x)).max() < 2e-6
+
+
+def test_mixture_loop_exp_fp64():
+    """mix_exp_accumulate: 2048-entry table, monic degree-3 polynomial, clamp at e = 1408 (a clamped term is
+    ~2^-1021 instead of the true, even smaller value: both are far below the slow-path threshold 2^-959)."""
+    rng = np.random.RandomState(5)
+    e = np.concatenate([rng.uniform(0, 60, 300000), rng.uniform(0, 1400, 100000), 10.0 ** rng.uniform(-12, 1, 50000),
+                        [0.0, 1e-300, 1407.9, 1408.0, 1500.0, 1e6, 1e12, 1e300, np.inf]])
+    got = run(5, e)
+    want = np.exp(-0.5 * e)
+    ok = e < 1400
+    rel = np.abs(got[ok] - want[ok]) / want[ok]
+    assert rel.max() < 5e-14                     # |z| 2^-53 argument rounding dominates near the edge
+    assert rel[e[ok] < 60].max() < 8e-15
+    assert np.all(got[~ok] < 2.0 ** -1000) and np.all(got[~ok] >= 0.0)  # clamped: tiny, finite, never wrapped
+    assert np.all(np.isnan(run(5, np.array([np.nan]))) | (run(5, np.array([np.nan])) < 2.0 ** -1000))
+
+
+def test_mixture_loop_log_fp64():
+    rng = np.random.RandomState(6)
+    x = np.concatenate([rng.uniform(1e-3, 8.0, 300000), 10.0 ** rng.uniform(-280, 300, 100000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 50000), [1.0, 2.0, 0.5, np.sqrt(2), 1 / np.sqrt(2),
+                                                                 1.4140625, 1.41406249, 0.70703125]])
+    got = run(6, x)
+    want = np.log(x.astype(np.longdouble)).astype(np.float64)
+    err = np.abs(got - want)
+    assert np.max(err / np.maximum(np.abs(want), 1.0)) < 6e-16  # absolute next to 1, relative elsewhere
+    assert got[300000 + 100000 + 50000] == 0.0                  # log(1) exact
