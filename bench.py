@@ -148,22 +148,35 @@ def algorithmic_bytes(kind, prm, rows_local, B, dtype):
 
 
 def fp64_view(kind, prm, rows_local, B, dtype, kern_ms, device):
-    """The mixture kernel is bound by the FP64 pipe, not by HBM: report how busy
-    that pipe is.  Numerator: FP64 instructions the kernel issues per (row, node) -- 115 for K=8, d=2,
-    counted in the SASS of the inner loop -- x rows x B; denominator: the FP64 FMA issue
-    rate measured on this GPU by pf_debug_fp64_probe (MEASURED_PEAKS.json has no FP64 figure)."""
-    if kind != "mixture" or dtype != "f64" or (prm["K"], prm["d"]) != (8, 2):
+    """How busy the FP64 pipe is (MEASURED_PEAKS.json has no FP64 figure: the denominator is the FP64 FMA rate
+    measured on this GPU by pf_debug_fp64_probe; the DMMA rate measured by pf_debug_dmma_probe is the same).
+    Mixture (bound by this pipe for every B): FP64 instructions issued per (row, node) --
+    100 for K=8, d=2, counted in the SASS of the inner loop (scripts/loopstat.sh) -- x rows x B.
+    Lasso / dense Boltzmann: FMAs of the contraction (rows x cols x B), issued as DMMA m8n8k4."""
+    if dtype != "f64":
+        return None
+    if kind == "mixture" and (prm["K"], prm["d"]) == (8, 2):
+        instr = 100.0 * rows_local * B
+        note = ("100 FP64 instructions per (row,node) from the inner-loop SASS; with the loop's 72 other instructions "
+                "the dispatch ceiling of this mix is 200/272 = 0.74 of the pipe (an FP64 instruction holds the "
+                "dispatch port 2 cycles, any other 1: scripts/fp64_probe.py)")
+    elif kind == "blasso":
+        instr = float(rows_local) * prm["p"] * B
+        note = "FMAs of the rows x p x B contraction, issued as DMMA m8n8k4 (HBM is the binding unit for B <= 16)"
+    elif kind == "boltzmann":
+        instr = float(prm["D"]) * prm["D"] * B
+        note = "FMAs of x'Wx for B nodes, issued as DMMA m8n8k4 (a ~20 us latency-bound call)"
+    else:
         return None
     import ctypes as C
     from fetching_b200 import _lib
     out = np.zeros(16)
     _lib.check(_lib.load().pf_debug_fp64_probe(device, out.ctypes.data_as(C.POINTER(C.c_double))), "fp64 probe")
     peak_tfma = float(out.max())
-    instr = 115.0 * rows_local * B
     achieved = instr / (kern_ms * 1e-3) / 1e12
     return {"bound": "fp64", "achieved": achieved, "peak": peak_tfma, "unit": "T FP64 instr-lanes/s (1 FMA = 1)",
             "frac": achieved / peak_tfma, "peak_tflops": 2 * peak_tfma,
-            "note": "peak measured by pf_debug_fp64_probe; 115 FP64 instr per (row,node) from the inner-loop SASS"}
+            "note": "peak measured by pf_debug_fp64_probe; " + note}
 
 
 # ------------------------------------------------------------------------------------------ clocks

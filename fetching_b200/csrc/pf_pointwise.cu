@@ -9,9 +9,10 @@
 //   metric_sum = sum_items lp_item,   metric_sum_sq = sum_items lp_item^2.
 //
 // DESIGN (B200).  The data set is read from HBM exactly once per launch, whatever the
-// frontier size B.  Each CTA owns a contiguous row range; a producer warp streams it through a
-// 4-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier tx counts), and
-// eight consumer warps score every staged row against every node.  Lanes are split
+// frontier size B.  Each CTA owns a contiguous row range, streamed through a 4-stage shared-memory
+// ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier tx counts) issued by one elected lane
+// (PF_PW_FOLD; a dedicated producer warp otherwise), and eight consumer warps score every staged row
+// against every node.  Lanes are split
 // NODES x POINT-LANES: lane l scores node (l mod NB) on the rows of point-lane (l / NB), so theta
 // lives in registers, row reads are shared-memory broadcasts, and per-node accumulators never
 // leave the lane.  For B > 32 each lane carries two nodes.  Reductions are fixed-order (warp
@@ -33,9 +34,21 @@
 
 namespace pf {
 
-constexpr int PW_CONSUMER_WARPS = 7;  // + 1 producer warp = 256 threads: two CTAs per SM fit at up to 128 registers
+#ifndef PF_PW_WARPS
+#define PF_PW_WARPS 8
+#endif
+constexpr int PW_CONSUMER_WARPS = PF_PW_WARPS;  // 8 warps = 256 threads: two CTAs per SM fit at up to 128 registers
 constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
-constexpr int PW_THREADS = PW_CONSUMERS + 32;  // + one producer warp
+// PF_PW_FOLD: no dedicated producer warp -- lane 0 of consumer warp 0 issues the TMA copies between its rows.
+// The register file is per SM sub-partition (16K registers each, warps dealt round-robin), so 2 CTAs x (7 + 1)
+// warps leave two sub-partitions with 4 consumer warps and two with 3 + an idle producer: the loaded ones
+// bound the kernel at 7/8 of its rate.  2 CTAs x 8 consumer warps put 4 on every sub-partition at 128 registers.
+// Measured (mixture N = 1e8): 7 + 1 warps 7.28 ms (B = 8) / 55.8 ms (B = 64); 8 folded 6.47 / 49.1 ms.
+#ifndef PF_PW_FOLD
+#define PF_PW_FOLD 1
+#endif
+constexpr bool PW_FOLD = PF_PW_FOLD != 0;
+constexpr int PW_THREADS = PW_CONSUMERS + (PW_FOLD ? 0 : 32);  // + one producer warp
 constexpr int PW_STAGES = 4;
 constexpr int PW_TILE_BYTES = 16384;
 constexpr int PW_STAGE_BYTES = PW_TILE_BYTES + 32;  // room for the 16-byte aligned copy window
@@ -432,7 +445,16 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     }
     __syncthreads();
 
-    if (warp == PW_CONSUMER_WARPS) {
+    // one tile's copy: rows [t0, t1) -> stage s, completion counted on full[s]
+    auto issue_tile = [&](unsigned long long t0, unsigned long long t1, unsigned s) {
+        const unsigned long long b0 = t0 * RB_BYTES, b1 = t1 * RB_BYTES;
+        const unsigned long long w0 = b0 & ~15ull, w1 = (b1 + 15ull) & ~15ull;
+        const unsigned bytes = (unsigned) (w1 - w0);
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(stage_base + s * PW_STAGE_BYTES, static_cast<const unsigned char*>(a.data) + w0, bytes, &full[s]);
+    };
+
+    if (!PW_FOLD && warp == PW_CONSUMER_WARPS) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
@@ -514,11 +536,41 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     ItemOwner own;
     own.init(r0, a.item_rows);
 
+    // folded producer (PW_FOLD): lane 0 of warp 0 fills all PW_STAGES stages up front; when tile t (>= 1) starts it
+    // sends tile t + PW_STAGES - 1 into the stage tile t - 1 used.  If the other warps have not released that stage
+    // yet, the copy is issued after this warp's rows of tile t instead (a tile is ~20 us of work, a copy ~2 us:
+    // no stage ever runs dry, and the issuing warp never waits at the top of a tile).
+    const bool issuer = PW_FOLD && tid == 0;
+    TileIter pit{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+    unsigned pu = 0;  // next tile to issue
+    if (issuer) {
+        unsigned long long p0, p1;
+        while (pu < PW_STAGES && pit.next(p0, p1)) {
+            issue_tile(p0, p1, pu % PW_STAGES);
+            ++pu;
+        }
+    }
+    auto try_issue = [&](unsigned t, bool block) {
+        // tile pu = t + PW_STAGES - 1 reuses the stage of tile t - 1 (its (pu / PW_STAGES - 1)-th release)
+        const unsigned s = pu % PW_STAGES;
+        const unsigned phase = ((pu / PW_STAGES) - 1) & 1;
+        if (block)
+            mbar_wait(&empty[s], phase);
+        else if (!mbar_try_wait(&empty[s], phase))
+            return false;
+        unsigned long long p0, p1;
+        if (pit.next(p0, p1)) issue_tile(p0, p1, s);
+        ++pu;
+        return true;
+    };
+
     TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
     unsigned long long t0, t1;
     unsigned t = 0;
     while (it.next(t0, t1)) {
         const unsigned s = t % PW_STAGES;
+        bool issue_pending = false;
+        if (issuer && t >= 1 && pu == t + PW_STAGES - 1 && pit.cur < pit.end_all) issue_pending = !try_issue(t, false);
         mbar_wait(&full[s], (t / PW_STAGES) & 1);
         const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB_BYTES) & 15ull);
         const unsigned nrows = (unsigned) (t1 - t0);
@@ -556,6 +608,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
             }
         }
+        if (issue_pending) try_issue(t, true);
         if constexpr (M::HAS_REDO) {
             if (acc_needs_slow_path(redo)) {  // cold: discard this lane's sums of the tile (they start at 0 per tile) and walk its rows again
 #pragma unroll
