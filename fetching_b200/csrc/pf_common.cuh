@@ -220,7 +220,8 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
 // ---------------------------------------------------------------------------------------------
 // Fused all-reduce over NVLink peer memory (see PeerXchg in pf_engine.h).  Called by the consumer
 // threads of the finalizing CTA with this rank's totals in (S, Q) of threads tid < B; returns the
-// totals over all ranks, summed in rank order (identical bits on every rank).
+// totals over all ranks, summed in rank order (identical bits on every rank) -- or, in gather mode (node split),
+// every node's sums from the one rank that scored it, to threads tid < gather_total.
 //   1. every rank stores its [S | Q] record into slot (seq & 1), row `rank`, of EVERY rank's buffer
 //      (plain peer stores, spread over the CTA), fences at system scope, then releases a flag = seq
 //      next to each record;
@@ -273,8 +274,14 @@ static __device__ __noinline__ double2 peer_allreduce(const PeerXchg x, unsigned
         }
     }
     named_bar_sync(bar_id, (int) nthreads);
-    if (tid < B) {
-        const double* mine = x.peers[x.rank] + slot_base;
+    const double* mine = x.peers[x.rank] + slot_base;
+    if (x.gather_per) {  // node split: output node tid was scored by rank tid / per as its column tid % per
+        if (tid < x.gather_total) {
+            const unsigned r = tid / x.gather_per, c = tid - r * x.gather_per;
+            S = ld_cg_f64(mine + (size_t) r * kXchgRec + c);
+            Q = ld_cg_f64(mine + (size_t) r * kXchgRec + kMaxNodesPerPass + c);
+        }
+    } else if (tid < B) {
         double s = 0.0, q = 0.0;
         for (unsigned r = 0; r < G; ++r) {
             s += ld_cg_f64(mine + (size_t) r * kXchgRec + tid);

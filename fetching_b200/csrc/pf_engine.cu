@@ -78,7 +78,9 @@ static NcclApi* nccl_api() {
 
 PeerXchg Engine::next_xchg() {
     PeerXchg x{};
-    if (peer_fused && nranks > 1 && !node_split) {
+    if (peer_fused && nranks > 1 && (!node_split || gather_per)) {
+        x.gather_per = node_split ? gather_per : 0;
+        x.gather_total = node_split ? gather_total : 0;
         x.peers = d_peers;
         x.status = reinterpret_cast<unsigned int*>(d_hout + 2 * kMaxNodesPerPass + 1);
         x.seq = ++xchg_seq;
@@ -387,13 +389,16 @@ static int peer_status(Engine& e) {
 // Node-split (small data sets): the data set is replicated on every GPU, rank r scores nodes
 // [r*per, (r+1)*per) with the ordinary single-GPU kernel, and one ncclAllGather of 2*per doubles per rank hands
 // every rank every node's sums.  No data-path reduction: a node's sums come from exactly one GPU.
+// node split through the in-kernel gather: peers attached, one record holds the frontier, nobody is idle, and the
+// model runs a frontier kernel with a finalizing CTA (not the data-free scalar Boltzmann)
+static bool node_split_fusable(const Engine& e, uint32_t B) {
+    const uint32_t G = (uint32_t) e.nranks, per = (B + G - 1) / G;
+    return e.peer_fused && e.peer_attached && B <= (uint32_t) kMaxNodesPerPass && (G - 1) * per < B &&
+           per <= e.max_frontier && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR;
+}
+
 static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                                 double* sum, double* sum_sq) {
-    NcclApi* n = nccl_api();
-    if (!n || !n->AllGather) {
-        set_error("ncclAllGather not available");
-        return PF_ERR_NCCL;
-    }
     PF_CUDA(cudaSetDevice(e.device));
     const uint32_t G = (uint32_t) e.nranks, per = (B + G - 1) / G;
     if (per > kMaxNodesPerPass) {
@@ -402,6 +407,36 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
     }
     const uint32_t lo = (uint32_t) e.rank * per;
     const uint32_t nloc = lo >= B ? 0 : (B - lo < per ? B - lo : per);
+    if (node_split_fusable(e, B) && n_items > 0 && first_item * e.item_rows < e.n_rows) {
+        // every rank has at least one node and the whole frontier fits one record: the frontier kernel of my slice
+        // stores its sums into every peer's exchange buffer and gathers everybody's itself (PeerXchg gather mode):
+        // one kernel, results + completion flag in mapped host memory
+        if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !all_identity_cov(e, thetas + (size_t) lo * e.theta_len, nloc);
+        const size_t tbytes = (size_t) nloc * e.theta_len * 8;
+        memcpy(e.h_theta, thetas + (size_t) lo * e.theta_len, tbytes);
+        PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
+        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(e.h_out + 2 * kMaxNodesPerPass);
+        e.done_seq = ++e.host_seq;
+        e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout + 2 * kMaxNodesPerPass);
+        e.gather_per = per;
+        e.gather_total = B;
+        int r = launch_model(e, nloc, e.d_theta, e.d_hout, first_item, n_items, e.stream);
+        e.gather_per = e.gather_total = 0;
+        e.done_flag = nullptr;
+        if (r != PF_OK) return r;
+        r = wait_flag(e, flag, e.done_seq);
+        if (r != PF_OK) return r;
+        if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
+        memcpy(sum, e.h_out, (size_t) B * 8);
+        memcpy(sum_sq, e.h_out + B, (size_t) B * 8);
+        return PF_OK;
+    }
+    NcclApi* n = nccl_api();
+    if (!n || !n->AllGather || !e.nccl_comm) {
+        set_error("node split of %u nodes over %d ranks needs the NCCL communicator (the in-kernel gather covers "
+                  "nranks <= B <= %d)", B, e.nranks, kMaxNodesPerPass);
+        return PF_ERR_NCCL;
+    }
     std::vector<double> s(per, 0.0), q(per, 0.0);
     if (nloc) {
         const bool was = e.node_split;
@@ -605,11 +640,21 @@ int pf_eval_frontier_device(pf_engine* pe, uint32_t B, const double* d_thetas, d
     }
     if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e.stream;
-    if (e.node_split && e.nranks > 1) {
-        pf::set_error("node-split evaluation is available on the host-pointer path only");
-        return PF_ERR_UNSUPPORTED;
-    }
     if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !e.assume_identity;
+    if (e.node_split && e.nranks > 1) {
+        if (!pf::node_split_fusable(e, B)) {
+            pf::set_error("node split on the device-pointer path needs the peer exchange and nranks <= B <= %d",
+                          pf::kMaxNodesPerPass);
+            return PF_ERR_UNSUPPORTED;
+        }
+        const uint32_t G = (uint32_t) e.nranks, per = (B + G - 1) / G, lo = (uint32_t) e.rank * per;
+        const uint32_t nloc = B - lo < per ? B - lo : per;
+        e.gather_per = per;
+        e.gather_total = B;
+        const int rr = pf::launch_model(e, nloc, d_thetas + (size_t) lo * e.theta_len, d_out, 0, e.n_items, s);
+        e.gather_per = e.gather_total = 0;
+        return rr;
+    }
     int r = pf::launch_model(e, B, d_thetas, d_out, 0, e.n_items, s);
     if (r != PF_OK) return r;
     return pf::allreduce_out(e, d_out, B, s);

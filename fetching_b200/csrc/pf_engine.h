@@ -25,6 +25,9 @@ struct PeerXchg {
     unsigned int* status;      // mapped host word, set to 1 when a peer did not show up in time
     unsigned long long seq;    // call number, identical on every rank
     unsigned int rank, nranks;
+    // NODE SPLIT (replicated data): gather instead of sum -- rank r scored nodes [r * gather_per, ...) of a
+    // frontier of gather_total nodes; output node b is record (b / gather_per), column (b % gather_per).  0: sum.
+    unsigned int gather_per, gather_total;
 };
 
 // Geometry of one launch of the pointwise (normal / mixture) kernels.
@@ -115,6 +118,7 @@ struct Engine {
     bool peer_fused = false;               // the exchange is attached and selected (PF_OPT_PEER_EXCHANGE)
     bool peer_attached = false;
     unsigned long long xchg_seq = 0;
+    unsigned gather_per = 0, gather_total = 0;  // set around a node-split launch (see PeerXchg)
     PeerXchg next_xchg();                  // arguments for the next launch (advances the call number)
     uint64_t launches = 0;
 };

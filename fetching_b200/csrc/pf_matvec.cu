@@ -450,24 +450,26 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
                        BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q);
+        unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {
             const double2 t = peer_allreduce(a.xchg, tid, B, MV_CONSUMERS, 1, red, S, Q);
             S = t.x;
             Q = t.y;
+            if (a.xchg.gather_per) Bout = a.xchg.gather_total;
         }
-        if ((unsigned) tid < B) {
+        if ((unsigned) tid < Bout) {
             if constexpr (BOLTZ) {
                 const double lp = -S * a.inv_temperature;  // one item: the whole energy
                 a.out[tid] = lp;
-                a.out[B + tid] = lp * lp;
+                a.out[Bout + tid] = lp * lp;
             } else {
                 a.out[tid] = S;
-                a.out[B + tid] = Q;
+                a.out[Bout + tid] = Q;
             }
         }
     }
     if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
-        if ((unsigned) tid < B) __threadfence_system();
+        if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
         named_bar_sync(1, MV_CONSUMERS);
         if (tid == 0) {
             *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;

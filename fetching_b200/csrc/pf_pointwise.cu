@@ -701,18 +701,20 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
                        B, red, PW_BAR_ALL, PW_CONSUMERS, S, Q);
+        unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {
             const double2 t = peer_allreduce(a.xchg, tid, B, PW_CONSUMERS, PW_BAR_ALL, red, S, Q);
             S = t.x;
             Q = t.y;
+            if (a.xchg.gather_per) Bout = a.xchg.gather_total;
         }
-        if ((unsigned) tid < B) {
+        if ((unsigned) tid < Bout) {
             a.out[tid] = S;
-            a.out[B + tid] = Q;
+            a.out[Bout + tid] = Q;
         }
     }
     if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
-        if ((unsigned) tid < B) __threadfence_system();
+        if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
         named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
         if (tid == 0) {
             *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;

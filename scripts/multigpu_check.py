@@ -89,10 +89,16 @@ for B in (64, 13, 3):
     single = eng.eval_frontier(thetas)
     pfd.init_engine_comm(eng)
     eng.set_option(fb.OPT_NODE_SPLIT, 1)
-    s, q = eng.eval_frontier(thetas)
+    s, q = eng.eval_frontier(thetas)                  # NCCL all-gather behind the slice kernel
     e1, e2 = rel(s, single[0]), rel(q, single[1])
+    pfd.init_engine_peers(eng)                        # in-kernel gather over peer memory where it applies
+    l0 = eng.launch_count
+    sp, qp = eng.eval_frontier(thetas)
+    fused = eng.launch_count - l0 == 1 and world <= B
+    ok &= rel(sp, s) < 1e-13 and rel(qp, q) < 1e-13
     if rank == 0:
-        print("node split B=%d over %d ranks: rel err sum %.2e sum_sq %.2e" % (B, world, e1, e2), flush=True)
+        print("node split B=%d over %d ranks: rel err sum %.2e sum_sq %.2e; peer gather vs NCCL gather %.1e (one kernel: %s)" %
+              (B, world, e1, e2, rel(sp, s), fused), flush=True)
     ok &= e1 < 1e-12 and e2 < 1e-12
     t = torch.from_numpy(np.stack([s, q])).cuda()
     t0 = t.clone()

@@ -110,6 +110,61 @@ def test_lasso_row_shards_exchange_device_path(fb):
             e.close()
 
 
+@pytest.mark.parametrize("G,B", [(2, 64), (4, 13), (8, 8), (3, 64), (4, 33)])
+def test_node_split_gather(fb, G, B):
+    """NODE SPLIT (small data set replicated on every rank): rank r scores nodes [r * ceil(B/G), ...) and the kernels
+    gather each other's sums through the same exchange buffers."""
+    from fetching_b200 import models
+    data, pos = models.mixture_dataset(60_000, 8, 2, seed=4)
+    thetas = models.mixture_thetas(pos, B, seed=B)
+    with fb.FrontierEngine.mixture(data, 8, 1000) as full:
+        fs, fq = full.eval_frontier(thetas)
+    engs = [fb.FrontierEngine.mixture(data, 8, 1000) for _ in range(G)]
+    try:
+        fb.peer_attach_local(engs)
+        for e in engs:
+            e.set_option(fb.OPT_NODE_SPLIT, 1)
+        l0 = [e.launch_count for e in engs]
+        res = run_ranks(engs, thetas, calls=3)
+        for e, l in zip(engs, l0):
+            assert e.launch_count - l == 3
+            e.peer_status()
+        for s, q in res:
+            # a node's sums come from exactly one kernel; a slice of fewer nodes runs another lane geometry than
+            # the full frontier (rows are summed in a different order), so: equal to rounding, and identical bits
+            # on every rank
+            assert rel(s, fs) < 1e-13 and rel(q, fq) < 1e-13
+            assert np.array_equal(s, res[0][0]) and np.array_equal(q, res[0][1])
+    finally:
+        for e in engs:
+            e.close()
+
+
+def test_node_split_gather_lasso_and_boltzmann(fb):
+    from fetching_b200 import models
+    X, y, beta = models.blasso_dataset(6000, 100, seed=1)
+    th = models.blasso_thetas(beta, 24, seed=2, scale=0.05)
+    W, Xs = models.boltzmann_dataset(256, 40, seed=3)
+    for make, thetas in ((lambda: fb.FrontierEngine.blasso(X, y, item_rows=500), th),
+                         (lambda: fb.FrontierEngine.boltzmann_dense(W), Xs)):
+        with make() as full:
+            fs, fq = full.eval_frontier(thetas)
+        engs = [make() for _ in range(4)]
+        try:
+            fb.peer_attach_local(engs)
+            for e in engs:
+                e.set_option(fb.OPT_NODE_SPLIT, 1)
+            res = run_ranks(engs, thetas, calls=2)
+            for s, q in res:
+                # the slice of a rank runs with a different node-block count than the full frontier: same IEEE
+                # operations per node, possibly another summation order over columns / CTAs
+                assert rel(s, fs) < 1e-12 and rel(q, fq) < 1e-12
+                assert np.array_equal(s, res[0][0])
+        finally:
+            for e in engs:
+                e.close()
+
+
 def test_exchange_option_needs_attachment(fb):
     from fetching_b200 import models
     data, pos = models.mixture_dataset(20_000, 8, 2, seed=0)
