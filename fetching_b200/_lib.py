@@ -21,6 +21,7 @@ OPT_ASSUME_IDENTITY_COV = 1
 OPT_NODE_SPLIT = 2
 OPT_PEER_EXCHANGE = 3
 OPT_MATVEC_TENSOR = 4
+OPT_INLINE_THETA = 5
 
 
 class ModelDesc(C.Structure):
@@ -77,6 +78,7 @@ SYMBOLS = {
                                               EVAL_FN, RANGE_FN, C.c_void_p, ROW_FN, JOB_FN, C.c_void_p,
                                               C.POINTER(ChainStats)]),
     "pf_eval_frontier": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp]),
+    "pf_eval_frontier_repeat": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp, C.c_uint32, _dp]),
     "pf_eval_frontier_range": (C.c_int, [C.c_void_p, C.c_uint32, _dp, C.c_uint64, C.c_uint64,
                                          C.POINTER(C.c_uint64), _dp, _dp]),
     "pf_eval_frontier_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -480,20 +481,29 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         const double* th = thetas + (size_t) b0 * e.theta_len;
         if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !all_identity_cov(e, th, nb);
         const size_t tbytes = (size_t) nb * e.theta_len * 8;
-        memcpy(e.h_theta, th, tbytes);
-        // (theta goes through a DMA copy: letting ~300 CTAs read it from mapped host memory was measured SLOWER,
-        // 56 vs 37 us per call for the normal target -- hundreds of small PCIe reads in front of the compute)
-        PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
         // Fast path: one frontier kernel whose last CTA writes the 2*nb results into mapped host memory and then
         // publishes a sequence number.  Row-sharded groups reduce inside the same kernel (peer_allreduce).  Not for NCCL-reduced results, ordered ranges, the scalar model or empty ranges.
         const bool fast = !order && (e.nranks <= 1 || peer_active(e)) && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR && n_items > 0 &&
                           first_item * e.item_rows < e.n_rows;
+        // Small frontiers of the pointwise models ride in the kernel parameters (PointwiseArgs::theta_inline); anything
+        // else goes through a DMA copy (letting ~300 CTAs read theta from mapped host memory was measured SLOWER,
+        // 56 vs 37 us per call for the normal target -- hundreds of small PCIe reads in front of the compute).
+        const bool inline_theta = fast && e.allow_inline_theta && (e.desc.model == PF_MODEL_NORMAL || e.desc.model == PF_MODEL_MIXTURE) &&
+                                  (size_t) nb * e.theta_len <= (size_t) kInlineThetaDoubles;
+        if (!inline_theta) {
+            memcpy(e.h_theta, th, tbytes);
+            PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
+        }
         int r;
         if (fast) {
+            e.inline_theta = inline_theta ? th : nullptr;
+            e.inline_theta_n = inline_theta ? (unsigned) (nb * e.theta_len) : 0;
             e.done_seq = ++e.host_seq;
             e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout + 2 * kMaxNodesPerPass);
             r = launch_model(e, nb, e.d_theta, e.d_hout, first_item, n_items, e.stream);
             e.done_flag = nullptr;
+            e.inline_theta = nullptr;
+            e.inline_theta_n = 0;
             if (r != PF_OK) return r;
             r = wait_flag(e, flag, e.done_seq);
             if (r != PF_OK) return r;
@@ -567,6 +577,7 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
         case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
         case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
         case PF_OPT_MATVEC_TENSOR: e.mv_tensor = value != 0; return PF_OK;
+        case PF_OPT_INLINE_THETA: e.allow_inline_theta = value != 0; return PF_OK;
         case PF_OPT_PEER_EXCHANGE:
             if (value != 0 && !e.peer_attached) {
                 pf::set_error("PF_OPT_PEER_EXCHANGE: no peer buffers attached (pf_engine_peer_attach)");
@@ -590,6 +601,24 @@ int pf_eval_frontier(pf_engine* pe, uint32_t B, const double* thetas, double* su
     }
     Engine& e = *reinterpret_cast<Engine*>(pe);
     return pf::eval_host(e, B, thetas, 0, e.n_items, nullptr, sum, sum_sq);
+}
+
+int pf_eval_frontier_repeat(pf_engine* pe, uint32_t B, const double* thetas, double* sum, double* sum_sq, uint32_t iters,
+                            double* seconds) {
+    if (!pe || !thetas || !sum || !sum_sq || B == 0 || iters == 0) {
+        pf::set_error("pf_eval_frontier_repeat: null argument, B == 0 or iters == 0");
+        return PF_ERR_INVALID;
+    }
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (uint32_t i = 0; i < iters; ++i) {
+        const int r = pf::eval_host(e, B, thetas, 0, e.n_items, nullptr, sum, sum_sq);
+        if (r != PF_OK) return r;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (seconds) *seconds = (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+    return PF_OK;
 }
 
 int pf_eval_frontier_range(pf_engine* pe, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,

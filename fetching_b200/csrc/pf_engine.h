@@ -11,6 +11,7 @@ namespace pf {
 constexpr int kMaxNodesPerPass = 64;  // frontier nodes scored by one kernel launch
 constexpr int kPartSlots = 4;        // per-CTA record: S, Q, head, tail
 constexpr int kMaxGrid = 148 * 4;    // upper bound on CTAs per launch (sizes the partial buffer)
+constexpr int kInlineThetaDoubles = 432;  // keeps PointwiseArgs under the classic 4 KB kernel-parameter limit
 constexpr int kXchgMaxRanks = 16;    // ranks in one peer-exchange group (one NVSwitch domain)
 constexpr int kXchgRec = 2 * kMaxNodesPerPass + 16;  // doubles per (slot, rank) record: S[64], Q[64], flag, pad
 constexpr int kXchgSlots = 2;        // records are double-buffered by call parity
@@ -46,6 +47,10 @@ struct PointwiseArgs {
     unsigned long long* done_flag;
     unsigned long long done_seq;
     PeerXchg xchg;
+    // host path, small frontiers: the thetas travel INSIDE the kernel parameters (constant bank, broadcast to every
+    // CTA) instead of through a host->device copy in front of the kernel (~8 us of a ~27 us call)
+    unsigned int theta_inline_n;          // doubles valid in theta_inline; 0: read `theta`
+    double theta_inline[kInlineThetaDoubles];
 };
 
 // Geometry of one launch of the streamed-matrix (lasso / dense Boltzmann) kernel.
@@ -119,6 +124,9 @@ struct Engine {
     bool peer_attached = false;
     unsigned long long xchg_seq = 0;
     unsigned gather_per = 0, gather_total = 0;  // set around a node-split launch (see PeerXchg)
+    const double* inline_theta = nullptr;        // set around a host-path launch: HOST thetas to pass as parameters
+    unsigned inline_theta_n = 0;
+    bool allow_inline_theta = true;              // PF_OPT_INLINE_THETA
     PeerXchg next_xchg();                  // arguments for the next launch (advances the call number)
     uint64_t launches = 0;
 };

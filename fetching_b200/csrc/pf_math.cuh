@@ -461,7 +461,10 @@ constexpr int kExpArgClampHi = 0x40960000;         // high word of 1408.0: -e/2 
 // ptxas re-materialises with two MOVs per iteration), and the leading coefficient B3 = ln2^3/6 lives in the table.
 constexpr double kExpQ2 = 4.328085122666891, kExpQ1 = 12.488213886033646, kExpQ0 = 18.016684242941434;
 // filled once per device by the host (pf_pointwise.cu: ensure_exp_table): long-double B3 2^(j/2048), high word - (j << 9)
-__device__ double g_exp2_big[kExpBigSize];
+__device__ __align__(16) double g_exp2_big[kExpBigSize];
+// ... and the log table as log_pos_fast_k wants it ({1/c_j doubled for j >= kLogTabFirstHalf, log c_j}), so that both
+// tables reach shared memory by one TMA bulk copy each instead of ten dependent loads per thread
+__device__ __align__(16) double g_log_adj[512];
 
 template <int G>
 __device__ __forceinline__ void mix_exp_accumulate(double (&e)[G], double& lp0, double& lp1, unsigned tab_s) {

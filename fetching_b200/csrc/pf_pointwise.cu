@@ -404,12 +404,12 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a);
 #define PF_PW_MAXOCC 2  // resident CTAs per SM actually used (a third one was measured slower: 80 vs 68 us, normal B=64)
 #endif
 template <class M, typename T, int NPL>
-__global__ void __launch_bounds__(PW_THREADS, PF_PW_BLOCKS) pw_frontier_kernel2(const PointwiseArgs a) {
+__global__ void __launch_bounds__(PW_THREADS, PF_PW_BLOCKS) pw_frontier_kernel2(const __grid_constant__ PointwiseArgs a) {
     pw_frontier_body<M, T, NPL>(a);
 }
 
 template <class M, typename T, int NPL>
-__global__ void __launch_bounds__(PW_THREADS, 1) pw_frontier_kernel1(const PointwiseArgs a) {
+__global__ void __launch_bounds__(PW_THREADS, 1) pw_frontier_kernel1(const __grid_constant__ PointwiseArgs a) {
     pw_frontier_body<M, T, NPL>(a);
 }
 
@@ -435,11 +435,13 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     if (r1 > a.row_end) r1 = a.row_end;
 
     __shared__ unsigned long long theta_nan;  // bit b: node b has a NaN in its theta (see mix_exp_accumulate)
+    __shared__ uint64_t tabbar;               // completion of the exp / log table copies (mixture, FP64)
     if (tid == 0) {
         for (int s = 0; s < PW_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], PW_CONSUMER_WARPS);
         }
+        mbar_init(&tabbar, 1);
         fence_barrier_init();
         theta_nan = 0ull;
     }
@@ -477,6 +479,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 
     // ---------------------------------------------------------------------- consumer warps
     const unsigned B = a.B;
+    // thetas: device memory, or the kernel parameters themselves (__grid_constant__: their address may be taken)
+    const double* const theta = a.theta_inline_n ? a.theta_inline : a.theta;
     unsigned NB = 32;  // node lanes (power of two >= min(B, 32))
     if (B < 32) {
         NB = 1;
@@ -498,21 +502,26 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         const unsigned raw_s = smem_u32(exp2_raw);
         double* const exp2_tab = BIG ? exp2_raw : exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
         if constexpr (BIG) {
-            for (int i = tid; i < kExpBigSize; i += PW_CONSUMERS) exp2_tab[i] = g_exp2_big[i];
+            // 16 KB + 4 KB by two TMA bulk copies (20 us -> 7 us of fixed cost per call against per-thread loads)
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&tabbar, (unsigned) (sizeof(double) * kExpBigSize + sizeof(double2) * 256));
+                bulk_g2s(exp2_tab, g_exp2_big, (unsigned) (sizeof(double) * kExpBigSize), &tabbar);
+                bulk_g2s(log_tab, g_log_adj, (unsigned) (sizeof(double2) * 256), &tabbar);
+            }
         } else {
             for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
+            for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
         }
-        for (int i = tid; i < 256; i += PW_CONSUMERS)  // log_pos_fast_k wants 1/c_j doubled in the upper half
-            log_tab[i] = make_double2(kLogTab[2 * i] * (BIG && i >= kLogTabFirstHalf ? 2.0 : 1.0), kLogTab[2 * i + 1]);
         const unsigned stride = theta_smem_stride<CT>(a.theta_len);
         for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
             const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
-            const double v = a.theta[i];
+            const double v = theta[i];
             th_smem[node * stride + j] = (CT) v;
             if constexpr (BIG)
                 if (v != v) atomicOr(&theta_nan, 1ull << node);
         }
         named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
+        if constexpr (BIG) mbar_wait(&tabbar, 0);
 #pragma unroll
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
@@ -524,7 +533,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
             if (node >= B) node = B - 1;
-            M::load(nd[n], a.theta + (size_t) node * a.theta_len, a.K);
+            M::load(nd[n], theta + (size_t) node * a.theta_len, a.K);
         }
     }
 
@@ -827,8 +836,7 @@ __global__ void debug_math_kernel_big(int which, const double* in, double* out, 
     __shared__ double tab[kExpBigSize];
     __shared__ __align__(16) double2 ltab[256];
     for (int k = threadIdx.x; k < kExpBigSize; k += blockDim.x) tab[k] = g_exp2_big[k];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x)
-        ltab[k] = make_double2(kLogTab[2 * k] * (k >= kLogTabFirstHalf ? 2.0 : 1.0), kLogTab[2 * k + 1]);
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) ltab[k] = make_double2(g_log_adj[2 * k], g_log_adj[2 * k + 1]);
     __syncthreads();
     if (i >= n) return;
     double r;
@@ -868,7 +876,14 @@ int ensure_exp_table(Engine& e) {
         bits -= (unsigned long long) ((unsigned) j << 9) << 32;
         memcpy(&host_tab[j], &bits, 8);
     }
-    if (cudaMemcpyToSymbol(g_exp2_big, host_tab, sizeof host_tab) != cudaSuccess) {
+    static double host_log[512];
+    if (cudaMemcpyFromSymbol(host_log, kLogTab, sizeof host_log) != cudaSuccess) {
+        set_error("download of the log table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    for (int j = kLogTabFirstHalf; j < 256; ++j) host_log[2 * j] *= 2.0;  // see log_pos_fast_k
+    if (cudaMemcpyToSymbol(g_log_adj, host_log, sizeof host_log) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_exp2_big, host_tab, sizeof host_tab) != cudaSuccess) {
         set_error("upload of the exp table failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
@@ -985,6 +1000,11 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     PointwiseArgs a{};
     a.data = e.d_data;
     a.theta = d_theta;
+    a.theta_inline_n = 0;
+    if (e.inline_theta && e.inline_theta_n <= (unsigned) kInlineThetaDoubles) {
+        a.theta_inline_n = e.inline_theta_n;
+        memcpy(a.theta_inline, e.inline_theta, (size_t) e.inline_theta_n * sizeof(double));
+    }
     a.part = e.d_part;
     a.out = d_out;
     a.ticket = e.d_ticket;

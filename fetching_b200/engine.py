@@ -100,6 +100,16 @@ class FrontierEngine:
                                          q.ctypes.data_as(_dp)), "pf_eval_frontier")
         return s, q
 
+    def eval_frontier_repeat(self, thetas, iters: int):
+        """`iters` complete host-buffer calls in a C loop; returns (sum, sum_sq, seconds)."""
+        t = self._thetas(thetas)
+        B = t.shape[0]
+        s, q = np.empty(B), np.empty(B)
+        sec = C.c_double(0.0)
+        check(self._lib.pf_eval_frontier_repeat(self._h, B, t.ctypes.data_as(_dp), s.ctypes.data_as(_dp),
+                                                q.ctypes.data_as(_dp), iters, C.byref(sec)), "pf_eval_frontier_repeat")
+        return s, q, float(sec.value)
+
     def eval_frontier_range(self, thetas, first_item: int, n_items: int, order=None):
         t = self._thetas(thetas)
         B = t.shape[0]

@@ -125,6 +125,12 @@ PF_API uint32_t pf_engine_components(const pf_engine* e);
  * of 2*B doubles, all on the engine's stream; returns when the results are in `sum`/`sum_sq`. */
 PF_API int pf_eval_frontier(pf_engine* e, uint32_t B, const double* thetas, double* sum, double* sum_sq);
 
+/* The same call `iters` times back to back (every iteration a complete pf_eval_frontier: theta from the host
+ * buffer, kernel, results back in `sum` / `sum_sq`), timed with the host's monotonic clock into *seconds.  What a
+ * C++ master's loop costs per burst, without a scripting language's per-call overhead in between (bench.py). */
+PF_API int pf_eval_frontier_repeat(pf_engine* e, uint32_t B, const double* thetas, double* sum, double* sum_sq,
+                            uint32_t iters, double* seconds);
+
 /* Same over items [first_item, first_item + n_items) only.  For PF_MODEL_NORMAL the items are
  * visited in the reference's per-node pseudo-random order when `order` is non-NULL:
  * order[2*b] = stride, order[2*b+1] = start of node b's StrideIndex (strideindex.hh:46-48,
@@ -246,7 +252,10 @@ enum pf_option {
     /* Lasso / dense Boltzmann, FP64: 1 (default) = contraction on the FP64 tensor cores (mma.sync.m8n8k4.f64,
      * DMMA), 0 = FP64 FMA on the CUDA cores (the variant PF_F32 always uses).  Same IEEE arithmetic,
      * different summation order over the columns. */
-    PF_OPT_MATVEC_TENSOR = 4
+    PF_OPT_MATVEC_TENSOR = 4,
+    /* Host-pointer calls of the pointwise models: 1 (default) = frontiers of up to 432 doubles of theta travel in
+     * the kernel parameters, 0 = always through a host->device copy in front of the kernel. */
+    PF_OPT_INLINE_THETA = 5
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 
