@@ -113,9 +113,11 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 // ---------------------------------------------------------------------------------------------
 struct ItemOwner {
     double S, Q, run, head, tail;
+    double stitch;  // index of the CTA in which the cut item that ENDS in this CTA began, or -1
     bool from_start, open;
     __device__ __forceinline__ void init(unsigned long long r0, unsigned long long item_rows) {
         S = Q = run = head = tail = 0.0;
+        stitch = -1.0;
         from_start = (item_rows <= 1) || (r0 % item_rows == 0);
         open = false;
     }
@@ -135,12 +137,24 @@ struct ItemOwner {
         }
         open = !closes;
     }
-    __device__ __forceinline__ void finish() {
+    // Called once per CTA with its row range [c0, c1): the 64-bit divisions that locate the beginning of a cut
+    // item are paid here, by every CTA in parallel, instead of in the finalizing CTA's serial tail.
+    __device__ __forceinline__ void finish(unsigned long long c0, unsigned long long c1, unsigned long long row_begin,
+                                           unsigned long long row_end, unsigned long long rows_per_cta,
+                                           unsigned long long item_rows) {
         if (open) {
             if (from_start)
                 tail = run;
             else
                 head = run;  // the whole CTA lies inside one item
+        }
+        if (item_rows > 1 && rows_per_cta && c1 > c0) {
+            const unsigned long long q0 = c0 / item_rows;
+            if (c0 != q0 * item_rows) {  // an item begun earlier reaches into this CTA
+                unsigned long long ie = (q0 + 1) * item_rows;
+                if (ie > row_end) ie = row_end;
+                if (ie <= c1) stitch = (double) ((q0 * item_rows - row_begin) / rows_per_cta);  // ... and ends here
+            }
         }
     }
     __device__ __forceinline__ void store(double* rec, unsigned tid) const {
@@ -148,15 +162,16 @@ struct ItemOwner {
         rec[1 * kMaxNodesPerPass + tid] = Q;
         rec[2 * kMaxNodesPerPass + tid] = head;
         rec[3 * kMaxNodesPerPass + tid] = tail;
+        rec[4 * kMaxNodesPerPass + tid] = stitch;
     }
 };
 
-// Finalize, run by the 256 consumer threads of the LAST CTA to finish.  Thread t works for node
-// (t mod BP) as worker (t / BP): it folds the records of CTAs worker, worker+NW, ... -- plain S/Q
-// sums plus, for every CTA in which a cut item ENDS, that item's stitched total
+// Finalize, run by the consumer threads of the LAST CTA to finish.  Thread t works for node (t mod BP) as worker
+// (t / BP): it folds the records of CTAs worker, worker+NW, ... -- plain S/Q sums plus, for every CTA in which a cut
+// item ENDS (record slot 4 names the CTA it began in), that item's stitched total
 //     tail(first CTA of the item) + head(next CTA) + ... + head(this CTA)
-// whose CTA span is known analytically, so all loads are independent (no serial carry chain) --
-// and the NW workers are then combined in worker order.  Fixed order => bit-stable.
+// -- and the NW workers are then combined in worker order.  Fixed order => bit-stable.  The S / Q / stitch loads of a
+// batch of 8 records are all issued before the first use (the tail of every call is this latency-bound loop).
 // `nthreads` consumer threads take part (tid < nthreads); `scratch` holds 2 * nthreads doubles.
 // Returns S/Q to threads tid < B.
 __device__ __forceinline__ void finalize_items(const double* part, unsigned grid, unsigned long long row_begin,
@@ -164,6 +179,7 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                                                unsigned long long item_rows, unsigned tid, unsigned B,
                                                double* scratch, int bar_id, unsigned nthreads, double& S_out,
                                                double& Q_out) {
+    constexpr size_t REC = (size_t) kPartSlots * kMaxNodesPerPass;
     unsigned BP = 64;
     if (B <= 32) {
         BP = 1;
@@ -178,27 +194,33 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
         const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
         if (n_cta < gmax) gmax = (unsigned) n_cta;
     }
-#pragma unroll 8
-    for (unsigned c = worker < NW ? worker : gmax; c < gmax; c += NW) {
-        const double* pr = part + (size_t) c * 4 * kMaxNodesPerPass + bb;
-        S += ld_cg_f64(pr);
-        Q += ld_cg_f64(pr + kMaxNodesPerPass);
-        if (item_rows > 1) {
-            const unsigned long long c0 = row_begin + (unsigned long long) c * rows_per_cta;
-            unsigned long long c1 = c0 + rows_per_cta;
-            if (c1 > row_end) c1 = row_end;
-            const unsigned long long q0 = c0 / item_rows;
-            if (c0 != q0 * item_rows) {  // an item begun earlier reaches into this CTA
-                unsigned long long ie = (q0 + 1) * item_rows;
-                if (ie > row_end) ie = row_end;
-                if (ie <= c1) {  // ... and ends here: stitch it
-                    const unsigned cs = (unsigned) ((q0 * item_rows - row_begin) / rows_per_cta);
-                    double tot = ld_cg_f64(part + (size_t) cs * 4 * kMaxNodesPerPass + 3 * kMaxNodesPerPass + bb);
-                    for (unsigned k = cs + 1; k <= c; ++k)
-                        tot += ld_cg_f64(part + (size_t) k * 4 * kMaxNodesPerPass + 2 * kMaxNodesPerPass + bb);
-                    S += tot;
-                    Q = fma(tot, tot, Q);
-                }
+    const bool stitching = item_rows > 1 && rows_per_cta;
+    constexpr int BATCH = 8;
+    for (unsigned c = worker < NW ? worker : gmax; c < gmax; c += BATCH * NW) {
+        double s[BATCH], q[BATCH], st[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const unsigned cu = c + u * NW;
+            const bool live = cu < gmax;
+            const double* pr = part + (size_t) (live ? cu : c) * REC + bb;
+            s[u] = ld_cg_f64(pr);
+            q[u] = ld_cg_f64(pr + kMaxNodesPerPass);
+            st[u] = stitching ? ld_cg_f64(pr + 4 * kMaxNodesPerPass) : -1.0;
+            if (!live) {
+                s[u] = q[u] = 0.0;
+                st[u] = -1.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            S += s[u];
+            Q += q[u];
+            if (st[u] >= 0.0) {  // a cut item ends in CTA cu: stitch it
+                const unsigned cu = c + u * NW, cs = (unsigned) st[u];
+                double tot = ld_cg_f64(part + (size_t) cs * REC + 3 * kMaxNodesPerPass + bb);
+                for (unsigned k = cs + 1; k <= cu; ++k) tot += ld_cg_f64(part + (size_t) k * REC + 2 * kMaxNodesPerPass + bb);
+                S += tot;
+                Q = fma(tot, tot, Q);
             }
         }
     }
@@ -235,6 +257,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+
+// diagnostics: time mark `i` of CTA 0 (row 0) or of the finalizing CTA (row 1); `tr` is nullptr in normal operation
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int row, int i, bool who) {
+    if (tr != nullptr && who) tr[row * 16 + i] = globaltimer_ns();
+}
+// ... and per CTA: [32 + 2 * cta] = kernel entry, [33 + 2 * cta] = record published
+__device__ __forceinline__ void trace_cta(unsigned long long* tr, int which, bool who) {
+    if (tr != nullptr && who) tr[32 + 2 * blockIdx.x + which] = globaltimer_ns();
 }
 
 static __device__ __noinline__ double2 peer_allreduce(const PeerXchg x, unsigned tid, unsigned B, unsigned nthreads,

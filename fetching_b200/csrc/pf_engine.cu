@@ -6,9 +6,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "pf_engine.h"
@@ -167,6 +169,7 @@ static void destroy(Engine* e) {
     cudaFree(e->d_peers);
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->h_trace) cudaFreeHost(e->h_trace);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -347,6 +350,11 @@ static int create(const pf_model_desc* d, Engine** out) {
     PF_CUDA_F(cudaHostAlloc(&e->h_out, 2 * kMaxNodesPerPass * 8 + 64, cudaHostAllocMapped));
     memset(e->h_out, 0, 2 * kMaxNodesPerPass * 8 + 64);
     PF_CUDA_F(cudaHostGetDevicePointer(&e->d_hout, e->h_out, 0));
+    if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1') {  // diagnostics: in-kernel time marks
+        PF_CUDA_F(cudaHostAlloc(&e->h_trace, (32 + 2 * kMaxGrid) * sizeof(unsigned long long), cudaHostAllocMapped));
+        memset(e->h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
+        PF_CUDA_F(cudaHostGetDevicePointer(&e->d_trace, e->h_trace, 0));
+    }
     PF_CUDA_F(cudaStreamSynchronize(e->stream));
 #undef PF_CUDA_F
     *out = e;
@@ -508,6 +516,33 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
             r = wait_flag(e, flag, e.done_seq);
             if (r != PF_OK) return r;
             if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
+            if (e.h_trace) {  // PF_TRACE=1: ns since CTA 0 entered the kernel
+                cudaStreamSynchronize(e.stream);
+                const unsigned long long* t = e.h_trace;
+                fprintf(stderr, "[pf trace] cta0: prologue %lld first-data %lld scored %lld units-done %lld published %lld | "
+                        "last cta: enter %lld folded %lld end %lld (ns)\n", (long long) (t[1] - t[0]), (long long) (t[2] - t[0]),
+                        (long long) (t[3] - t[0]), (long long) (t[4] - t[0]), (long long) (t[5] ? t[5] - t[0] : 0),
+                        (long long) (t[16] - t[0]), (long long) (t[17] - t[0]), (long long) (t[18] - t[0]));
+                std::vector<long long> in, out;
+                for (int c = 0; c < kMaxGrid; ++c)
+                    if (t[32 + 2 * c]) {
+                        in.push_back((long long) (t[32 + 2 * c] - t[0]));
+                        out.push_back((long long) (t[33 + 2 * c] - t[0]));
+                    }
+                if (!in.empty()) {
+                    std::sort(in.begin(), in.end());
+                    std::sort(out.begin(), out.end());
+                    fprintf(stderr, "[pf trace] %zu CTAs: entry min/med/max %lld/%lld/%lld, published min/med/max %lld/%lld/%lld (ns)\n",
+                            in.size(), in.front(), in[in.size() / 2], in.back(), out.front(), out[out.size() / 2], out.back());
+                }
+                if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1' && tr[1] == '1') {  // PF_TRACE=11: every CTA
+                    fprintf(stderr, "[pf trace] published(us) by CTA:");
+                    for (int c = 0; c < kMaxGrid; ++c)
+                        if (t[32 + 2 * c]) fprintf(stderr, " %.1f", (double) (long long) (t[33 + 2 * c] - t[0]) * 1e-3);
+                    fprintf(stderr, "\n");
+                }
+                memset(e.h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
+            }
             memcpy(sum + b0, e.h_out, (size_t) nb * 8);
             memcpy(sum_sq + b0, e.h_out + nb, (size_t) nb * 8);
             continue;

@@ -9,7 +9,7 @@
 namespace pf {
 
 constexpr int kMaxNodesPerPass = 64;  // frontier nodes scored by one kernel launch
-constexpr int kPartSlots = 4;        // per-CTA record: S, Q, head, tail
+constexpr int kPartSlots = 5;        // per-CTA record: S, Q, head, tail, stitch source (see ItemOwner)
 constexpr int kMaxGrid = 148 * 4;    // upper bound on CTAs per launch (sizes the partial buffer)
 constexpr int kInlineThetaDoubles = 432;  // keeps PointwiseArgs under the classic 4 KB kernel-parameter limit
 constexpr int kXchgMaxRanks = 16;    // ranks in one peer-exchange group (one NVSwitch domain)
@@ -49,6 +49,8 @@ struct PointwiseArgs {
     PeerXchg xchg;
     // host path, small frontiers: the thetas travel INSIDE the kernel parameters (constant bank, broadcast to every
     // CTA) instead of through a host->device copy in front of the kernel (~8 us of a ~27 us call)
+    unsigned long long* trace;            // diagnostics (PF_TRACE=1): %globaltimer marks of CTA 0 [0..15] and of the
+                                          // finalizing CTA [16..31]; nullptr in normal operation
     unsigned int theta_inline_n;          // doubles valid in theta_inline; 0: read `theta`
     double theta_inline[kInlineThetaDoubles];
 };
@@ -76,6 +78,7 @@ struct MatvecArgs {
     unsigned long long* done_flag;    // see PointwiseArgs
     unsigned long long done_seq;
     PeerXchg xchg;
+    unsigned long long* trace;        // see PointwiseArgs
 };
 
 struct Engine {
@@ -127,6 +130,8 @@ struct Engine {
     const double* inline_theta = nullptr;        // set around a host-path launch: HOST thetas to pass as parameters
     unsigned inline_theta_n = 0;
     bool allow_inline_theta = true;              // PF_OPT_INLINE_THETA
+    unsigned long long* h_trace = nullptr;       // PF_TRACE=1: mapped pinned [32] (+ device alias)
+    unsigned long long* d_trace = nullptr;
     PeerXchg next_xchg();                  // arguments for the next launch (advances the call number)
     uint64_t launches = 0;
 };

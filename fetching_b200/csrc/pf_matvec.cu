@@ -164,6 +164,9 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     UnitIter<BOLTZ> proto{r0, r1, a.item_rows, a.row_end, blockIdx.x, a.n_units, gridDim.x, a.k_splits,
                           a.chunks_per_split, n_chunks, tile_rows, a.row_begin};
 
+    const bool tr0 = tid == 0 && blockIdx.x == 0;
+    trace_mark(a.trace, 0, 0, tr0);
+    trace_cta(a.trace, 0, tid == 0);
     if (tid == 0) {
         for (int s = 0; s < MV_STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         for (unsigned c = c0; c < c1; ++c, ++q) {
             const unsigned s = q % MV_STAGES;
             mbar_wait(&full[s], (q / MV_STAGES) & 1);
+            if (q == 0) trace_mark(a.trace, 0, 2, tr0);  // first box landed
             if constexpr (MMA) {
                 // A[row = lane/4][k = lane%4] of row block mb, k-step ks: 16-byte chunk (2 ks + (lane%4)/2) of the
                 // row, swizzled with row & 7 == lane / 4 (row blocks start at multiples of 8), half lane & 1
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
+        if (unit == 0) trace_mark(a.trace, 0, 3, tr0);  // first unit's contraction done
         // ---- epilogue for this unit, in registers.  A lasso tile may contain ONE item boundary `ts`
         // (items are at least a tile tall in that mode): rows before it go to partA, rows after to partB.
         unsigned long long ts = t1;
@@ -430,9 +435,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         ++unit;
     }
 
+    trace_mark(a.trace, 0, 4, tr0);  // all units done (epilogues included)
     double* rec = a.part + (size_t) blockIdx.x * kPartSlots * kMaxNodesPerPass;
     if ((unsigned) tid < B) {
-        if constexpr (!BOLTZ) own.finish();
+        if constexpr (!BOLTZ) own.finish(r0, r1, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows);
         own.store(rec, tid);
         __threadfence();
     }
@@ -442,14 +448,18 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         flag[0] = (prev == gridDim.x - 1);
     }
     named_bar_sync(1, MV_CONSUMERS);
+    trace_mark(a.trace, 0, 5, tr0);  // record published
+    trace_cta(a.trace, 1, tid == 0);
     if (!flag[0]) return;
 
+    trace_mark(a.trace, 1, 0, tid == 0);
     __threadfence();
     {
         // Boltzmann: the records hold plain energy partials (one item): finalize with item_rows = 1
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
                        BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q);
+        trace_mark(a.trace, 1, 1, tid == 0);  // records folded
         unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {
             const double2 t = peer_allreduce(a.xchg, tid, B, MV_CONSUMERS, 1, red, S, Q);
@@ -471,12 +481,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
         if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
         named_bar_sync(1, MV_CONSUMERS);
-        if (tid == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
-            __threadfence_system();
-        }
+        if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
     }
     if (tid == 0) *a.ticket = 0u;
+    trace_mark(a.trace, 1, 2, tid == 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -652,6 +660,7 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
     a.xchg = e.next_xchg();
+    a.trace = e.d_trace;
     if (a.row_end <= a.row_begin) {
         cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
         return 0;

@@ -436,6 +436,9 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 
     __shared__ unsigned long long theta_nan;  // bit b: node b has a NaN in its theta (see mix_exp_accumulate)
     __shared__ uint64_t tabbar;               // completion of the exp / log table copies (mixture, FP64)
+    const bool tr0 = tid == 0 && blockIdx.x == 0;
+    trace_mark(a.trace, 0, 0, tr0);
+    trace_cta(a.trace, 0, tid == 0);
     if (tid == 0) {
         for (int s = 0; s < PW_STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -540,6 +543,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     double accS[NPL], accQ[NPL];
 #pragma unroll
     for (int n = 0; n < NPL; ++n) accS[n] = accQ[n] = 0.0;
+    trace_mark(a.trace, 0, 1, tr0);  // prologue done (tables, thetas)
 
     // owner-thread state (thread b < B assembles node b's item totals)
     ItemOwner own;
@@ -581,6 +585,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         bool issue_pending = false;
         if (issuer && t >= 1 && pu == t + PW_STAGES - 1 && pit.cur < pit.end_all) issue_pending = !try_issue(t, false);
         mbar_wait(&full[s], (t / PW_STAGES) & 1);
+        if (t == 0) trace_mark(a.trace, 0, 2, tr0);  // first tile landed
         const unsigned char* base = stage_base + s * PW_STAGE_BYTES + (unsigned) ((t0 * RB_BYTES) & 15ull);
         const unsigned nrows = (unsigned) (t1 - t0);
         // rows in flight per lane: batches of RB rows with every shared-memory load issued before the first use
@@ -665,6 +670,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         ++t;
     }
 
+    trace_mark(a.trace, 0, 3, tr0);  // all tiles scored
     double* rec = a.part + (size_t) blockIdx.x * kPartSlots * kMaxNodesPerPass;
     if constexpr (M::ITEM1) {
         // one block reduction at the very end: every row is its own item
@@ -689,7 +695,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             }
         }
     } else if ((unsigned) tid < B)
-        own.finish();
+        own.finish(r0, r1, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows);
     if ((unsigned) tid < B) {
         if constexpr (big_exp_table<M>())
             if ((theta_nan >> tid) & 1ull) own.S = own.Q = __longlong_as_double(0x7FF8000000000000ll);
@@ -702,14 +708,18 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         flag[0] = (prev == gridDim.x - 1);
     }
     named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
+    trace_mark(a.trace, 0, 4, tr0);  // record published
+    trace_cta(a.trace, 1, tid == 0);
     if (!flag[0]) return;
 
     // ---------------------------------------------------------------------- last CTA: finalize
+    trace_mark(a.trace, 1, 0, tid == 0);
     __threadfence();
     {
         double S, Q;
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, M::ITEM1 ? 1ull : a.item_rows, tid,
                        B, red, PW_BAR_ALL, PW_CONSUMERS, S, Q);
+        trace_mark(a.trace, 1, 1, tid == 0);  // records folded
         unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {
             const double2 t = peer_allreduce(a.xchg, tid, B, PW_CONSUMERS, PW_BAR_ALL, red, S, Q);
@@ -725,12 +735,10 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
         if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
         named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
-        if (tid == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
-            __threadfence_system();
-        }
+        if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
     }
     if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
+    trace_mark(a.trace, 1, 2, tid == 0);
 }
 
 
@@ -1000,6 +1008,7 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     PointwiseArgs a{};
     a.data = e.d_data;
     a.theta = d_theta;
+    a.trace = e.d_trace;
     a.theta_inline_n = 0;
     if (e.inline_theta && e.inline_theta_n <= (unsigned) kInlineThetaDoubles) {
         a.theta_inline_n = e.inline_theta_n;

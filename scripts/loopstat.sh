@@ -1,4 +1,6 @@
-cuobjdump -sass ${1:-fetching_b200/lib/libpfetch.so} | awk '/Function : .*pw_frontier_kernel2INS_12MixtureModelILi8ELi2EdEEdLi1E/{f=1} f{print}' | awk 'NR>1 && /Function :/{exit} {print}' > /tmp/mix.sass
+# usage: scripts/loopstat.sh [lib.so] [nodes-per-lane 1|2]: instruction mix of the mixture kernel's hot row loop
+pat="pw_frontier_kernel2INS_12MixtureModelILi8ELi2EdEEdLi${2:-1}E"
+cuobjdump -sass ${1:-fetching_b200/lib/libpfetch.so} | awk -v pat="$pat" '$0 ~ "Function : .*" pat {f=1} f{print}' | awk 'NR>1 && /Function :/{exit} {print}' > /tmp/mix.sass
 python3 - <<'PY'
 import re
 lines=[l for l in open('/tmp/mix.sass') if re.search(r'/\*[0-9a-f]{4}\*/',l)]
@@ -16,7 +18,7 @@ for i,(a,t) in enumerate(ins):
         if tgt<a and tgt in addr:
             body=ins[addr[tgt]:i+1]
             nd=sum(1 for _,x in body if re.search(r'\bD(FMA|ADD|MUL)\b',x))
-            ok=any('I2F' in x for _,x in body) and not any('CALL' in x for _,x in body)
+            ok=any('I2F' in x for _,x in body) and not any('CALL' in x for _,x in body) and not any('BAR' in x for _,x in body)
             if ok and nd>=60 and (best is None or len(body)<len(best[1])): best=(nd,body)
 nd,body=best
 from collections import Counter
