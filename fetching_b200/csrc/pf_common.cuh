@@ -114,18 +114,22 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 struct ItemOwner {
     double S, Q, run, head, tail;
     double stitch;  // index of the CTA in which the cut item that ENDS in this CTA began, or -1
+    unsigned long long next_close;  // the next item boundary after the rows folded so far (no modulo per tile)
     bool from_start, open;
     __device__ __forceinline__ void init(unsigned long long r0, unsigned long long item_rows) {
         S = Q = run = head = tail = 0.0;
         stitch = -1.0;
         from_start = (item_rows <= 1) || (r0 % item_rows == 0);
+        next_close = item_rows <= 1 ? r0 + 1 : (r0 / item_rows + 1) * item_rows;
         open = false;
     }
-    // `tot` = this node's total over tile [.., t1)
+    // `tot` = this node's total over tile [.., t1); tiles arrive in row order and never straddle an item
     __device__ __forceinline__ void add_tile(double tot, unsigned long long t1, unsigned long long item_rows,
                                              unsigned long long row_end) {
         run += tot;
-        const bool closes = (t1 % item_rows == 0) || (t1 == row_end);
+        const bool at_boundary = t1 >= next_close;
+        if (at_boundary) next_close += item_rows;
+        const bool closes = at_boundary || (t1 == row_end);
         if (closes) {
             if (from_start) {
                 S += run;

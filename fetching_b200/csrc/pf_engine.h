@@ -55,6 +55,8 @@ struct PointwiseArgs {
     double theta_inline[kInlineThetaDoubles];
 };
 
+static_assert(sizeof(PointwiseArgs) <= 4096, "PointwiseArgs must fit the classic kernel-parameter limit");
+
 // Geometry of one launch of the streamed-matrix (lasso / dense Boltzmann) kernel.
 struct MatvecArgs {
     CUtensorMap tmap;       // [rows][cols_pad] matrix, box = 16 doubles (or 32 floats) x ROWS, 128B swizzle

@@ -357,15 +357,20 @@ struct MixtureModelRT {
 struct TileIter {
     unsigned long long cur, end_all, item_rows, row_end;
     unsigned tile_rows;
+    unsigned long long item_end;  // end of the item `cur` lies in (0: not computed yet) -- one division per CTA,
+                                  // not one per tile: at B = 1 a tile is only four row iterations per warp
     __device__ __forceinline__ bool next(unsigned long long& t0, unsigned long long& t1) {
         if (cur >= end_all) return false;
         t0 = cur;
         unsigned long long e = cur + tile_rows;
         if (e > end_all) e = end_all;
         if (item_rows > 1) {
-            unsigned long long ie = (cur / item_rows + 1) * item_rows;
-            if (ie > row_end) ie = row_end;
-            if (e > ie) e = ie;
+            if (item_end == 0) item_end = (cur / item_rows + 1) * item_rows;
+            const unsigned long long ie = item_end < row_end ? item_end : row_end;
+            if (e >= ie) {
+                e = ie;
+                item_end += item_rows;
+            }
         }
         t1 = e;
         cur = e;
@@ -462,7 +467,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     if (!PW_FOLD && warp == PW_CONSUMER_WARPS) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
-            TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+            TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS, 0ull};
             unsigned long long t0, t1;
             unsigned t = 0;
             while (it.next(t0, t1)) {
@@ -554,7 +559,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     // yet, the copy is issued after this warp's rows of tile t instead (a tile is ~20 us of work, a copy ~2 us:
     // no stage ever runs dry, and the issuing warp never waits at the top of a tile).
     const bool issuer = PW_FOLD && tid == 0;
-    TileIter pit{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+    TileIter pit{r0, r1, a.item_rows, a.row_end, TILE_ROWS, 0ull};
     unsigned pu = 0;  // next tile to issue
     if (issuer) {
         unsigned long long p0, p1;
@@ -577,7 +582,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         return true;
     };
 
-    TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS};
+    TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS, 0ull};
     unsigned long long t0, t1;
     unsigned t = 0;
     while (it.next(t0, t1)) {
