@@ -263,6 +263,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// Result delivery of the host path: value i of n as two self-validating 8-byte words (see PointwiseArgs::done_flag).
+__device__ __forceinline__ void store_result_words(double* out, unsigned i, double v, unsigned long long seq) {
+    volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(out) + 2 * (size_t) i;
+    const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
+    w[0] = tag | (unsigned) __double2loint(v);
+    w[1] = tag | (unsigned) __double2hiint(v);
+}
+
 // diagnostics: time mark `i` of CTA 0 (row 0) or of the finalizing CTA (row 1); `tr` is nullptr in normal operation
 __device__ __forceinline__ void trace_mark(unsigned long long* tr, int row, int i, bool who) {
     if (tr != nullptr && who) tr[row * 16 + i] = globaltimer_ns();

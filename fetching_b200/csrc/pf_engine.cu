@@ -85,7 +85,7 @@ PeerXchg Engine::next_xchg() {
         x.gather_per = node_split ? gather_per : 0;
         x.gather_total = node_split ? gather_total : 0;
         x.peers = d_peers;
-        x.status = reinterpret_cast<unsigned int*>(d_hout + 2 * kMaxNodesPerPass + 1);
+        x.status = reinterpret_cast<unsigned int*>(d_hout + kHostOutWords + 1);
         x.seq = ++xchg_seq;
         x.rank = (unsigned) rank;
         x.nranks = (unsigned) nranks;
@@ -347,8 +347,8 @@ static int create(const pf_model_desc* d, Engine** out) {
     PF_CUDA_F(cudaMemsetAsync(e->d_ticket, 0, 64, e->stream));
     PF_CUDA_F(cudaHostAlloc(&e->h_theta, tbytes, cudaHostAllocMapped));
     PF_CUDA_F(cudaHostGetDevicePointer(&e->d_htheta, e->h_theta, 0));
-    PF_CUDA_F(cudaHostAlloc(&e->h_out, 2 * kMaxNodesPerPass * 8 + 64, cudaHostAllocMapped));
-    memset(e->h_out, 0, 2 * kMaxNodesPerPass * 8 + 64);
+    PF_CUDA_F(cudaHostAlloc(&e->h_out, (kHostOutWords + 8 + 2 * kMaxNodesPerPass) * 8, cudaHostAllocMapped));
+    memset(e->h_out, 0, (kHostOutWords + 8 + 2 * kMaxNodesPerPass) * 8);
     PF_CUDA_F(cudaHostGetDevicePointer(&e->d_hout, e->h_out, 0));
     if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1') {  // diagnostics: in-kernel time marks
         PF_CUDA_F(cudaHostAlloc(&e->h_trace, (32 + 2 * kMaxGrid) * sizeof(unsigned long long), cudaHostAllocMapped));
@@ -361,25 +361,44 @@ static int create(const pf_model_desc* d, Engine** out) {
     return PF_OK;
 }
 
-// Wait for the kernel's completion flag in mapped host memory (polling beats copy + synchronise by
-// ~15 us per call); falls back to the stream's status so that a failed kernel cannot hang the caller.
-static int wait_flag(Engine& e, volatile unsigned long long* flag, unsigned long long seq) {
-    for (unsigned long long spins = 1;; ++spins) {
-        if (*flag == seq) return PF_OK;
-        __builtin_ia32_pause();
-        if ((spins & 0x3FFFF) == 0) {
-            const cudaError_t q = cudaStreamQuery(e.stream);
-            if (q == cudaSuccess) {
-                if (*flag == seq) return PF_OK;
-                set_error("kernel finished without publishing its completion flag");
-                return PF_ERR_CUDA;
+// Collect the n result doubles the kernel's last CTA delivers as self-validating words in mapped host memory
+// (PointwiseArgs::done_flag): polling beats copy + synchronise by ~15 us per call and needs no fence on the device
+// side; falls back to the stream's status so that a failed kernel cannot hang the caller.
+static int wait_words(Engine& e, unsigned n, unsigned long long seq, double* vals) {
+    volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(e.h_out);
+    const unsigned long long tag = seq & 0xFFFFFFFFull;
+    unsigned long long spins = 0;
+    for (unsigned i = 0; i < n; ++i) {
+        for (;;) {
+            const unsigned long long lo = w[2 * i], hi = w[2 * i + 1];
+            if ((lo >> 32) == tag && (hi >> 32) == tag) {
+                const unsigned long long bits = (hi << 32) | (lo & 0xFFFFFFFFull);
+                memcpy(&vals[i], &bits, 8);
+                break;
             }
-            if (q != cudaErrorNotReady) {
-                set_error("stream error while waiting for the frontier kernel: %s", cudaGetErrorString(q));
-                return PF_ERR_CUDA;
+            __builtin_ia32_pause();
+            if ((++spins & 0x3FFFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(e.stream);
+                if (q == cudaSuccess) {
+                    const unsigned long long lo2 = w[2 * i], hi2 = w[2 * i + 1];
+                    if ((lo2 >> 32) == tag && (hi2 >> 32) == tag) continue;
+                    set_error("kernel finished without delivering its results");
+                    return PF_ERR_CUDA;
+                }
+                if (q != cudaErrorNotReady) {
+                    set_error("stream error while waiting for the frontier kernel: %s", cudaGetErrorString(q));
+                    return PF_ERR_CUDA;
+                }
             }
         }
     }
+    return PF_OK;
+}
+
+// a call number whose low 32 bits are never 0 (the tag of the result words; the buffer starts zeroed)
+static unsigned long long next_host_seq(Engine& e) {
+    if ((++e.host_seq & 0xFFFFFFFFull) == 0) ++e.host_seq;
+    return e.host_seq;
 }
 
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
@@ -387,7 +406,7 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
 
 // the word after the completion flag in mapped host memory: set by peer_allreduce() on a timeout
 static int peer_status(Engine& e) {
-    volatile unsigned int* st = reinterpret_cast<unsigned int*>(e.h_out + 2 * kMaxNodesPerPass + 1);
+    volatile unsigned int* st = reinterpret_cast<unsigned int*>(e.h_out + kHostOutWords + 1);
     if (*st) {
         set_error("peer exchange timed out: a rank of the group did not reach this frontier call");
         return PF_ERR_NCCL;
@@ -424,20 +443,20 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
         const size_t tbytes = (size_t) nloc * e.theta_len * 8;
         memcpy(e.h_theta, thetas + (size_t) lo * e.theta_len, tbytes);
         PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
-        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(e.h_out + 2 * kMaxNodesPerPass);
-        e.done_seq = ++e.host_seq;
-        e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout + 2 * kMaxNodesPerPass);
+        e.done_seq = next_host_seq(e);
+        e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout);
         e.gather_per = per;
         e.gather_total = B;
         int r = launch_model(e, nloc, e.d_theta, e.d_hout, first_item, n_items, e.stream);
         e.gather_per = e.gather_total = 0;
         e.done_flag = nullptr;
         if (r != PF_OK) return r;
-        r = wait_flag(e, flag, e.done_seq);
+        double vals[2 * kMaxNodesPerPass];
+        r = wait_words(e, 2 * B, e.done_seq, vals);
         if (r != PF_OK) return r;
         if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
-        memcpy(sum, e.h_out, (size_t) B * 8);
-        memcpy(sum_sq, e.h_out + B, (size_t) B * 8);
+        memcpy(sum, vals, (size_t) B * 8);
+        memcpy(sum_sq, vals + B, (size_t) B * 8);
         return PF_OK;
     }
     NcclApi* n = nccl_api();
@@ -483,7 +502,6 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
                      const uint64_t* order, double* sum, double* sum_sq) {
     if (e.node_split && e.nranks > 1 && !order) return eval_host_node_split(e, B, thetas, first_item, n_items, sum, sum_sq);
     PF_CUDA(cudaSetDevice(e.device));
-    volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(e.h_out + 2 * kMaxNodesPerPass);
     for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
         const uint32_t nb = B - b0 < e.max_frontier ? B - b0 : e.max_frontier;
         const double* th = thetas + (size_t) b0 * e.theta_len;
@@ -506,14 +524,15 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         if (fast) {
             e.inline_theta = inline_theta ? th : nullptr;
             e.inline_theta_n = inline_theta ? (unsigned) (nb * e.theta_len) : 0;
-            e.done_seq = ++e.host_seq;
-            e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout + 2 * kMaxNodesPerPass);
+            e.done_seq = next_host_seq(e);
+            e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout);
             r = launch_model(e, nb, e.d_theta, e.d_hout, first_item, n_items, e.stream);
             e.done_flag = nullptr;
             e.inline_theta = nullptr;
             e.inline_theta_n = 0;
             if (r != PF_OK) return r;
-            r = wait_flag(e, flag, e.done_seq);
+            double vals[2 * kMaxNodesPerPass];
+            r = wait_words(e, 2 * nb, e.done_seq, vals);
             if (r != PF_OK) return r;
             if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
             if (e.h_trace) {  // PF_TRACE=1: ns since CTA 0 entered the kernel
@@ -543,8 +562,8 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
                 }
                 memset(e.h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
             }
-            memcpy(sum + b0, e.h_out, (size_t) nb * 8);
-            memcpy(sum_sq + b0, e.h_out + nb, (size_t) nb * 8);
+            memcpy(sum + b0, vals, (size_t) nb * 8);
+            memcpy(sum_sq + b0, vals + nb, (size_t) nb * 8);
             continue;
         }
         if (order) {  // the reference's per-node visiting order (normal target; checked by the caller)
@@ -559,10 +578,11 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         if (r != PF_OK) return r;
         r = allreduce_out(e, e.d_out, nb, e.stream);
         if (r != PF_OK) return r;
-        PF_CUDA(cudaMemcpyAsync(e.h_out, e.d_out, (size_t) 2 * nb * 8, cudaMemcpyDeviceToHost, e.stream));
+        double* stage = e.h_out + kHostOutWords + 8;  // behind the result words and the status word
+        PF_CUDA(cudaMemcpyAsync(stage, e.d_out, (size_t) 2 * nb * 8, cudaMemcpyDeviceToHost, e.stream));
         PF_CUDA(cudaStreamSynchronize(e.stream));
-        memcpy(sum + b0, e.h_out, (size_t) nb * 8);
-        memcpy(sum_sq + b0, e.h_out + nb, (size_t) nb * 8);
+        memcpy(sum + b0, stage, (size_t) nb * 8);
+        memcpy(sum_sq + b0, stage + nb, (size_t) nb * 8);
     }
     return PF_OK;
 }

@@ -12,6 +12,7 @@ constexpr int kMaxNodesPerPass = 64;  // frontier nodes scored by one kernel lau
 constexpr int kPartSlots = 5;        // per-CTA record: S, Q, head, tail, stitch source (see ItemOwner)
 constexpr int kMaxGrid = 148 * 4;    // upper bound on CTAs per launch (sizes the partial buffer)
 constexpr int kInlineThetaDoubles = 432;  // keeps PointwiseArgs under the classic 4 KB kernel-parameter limit
+constexpr int kHostOutWords = 4 * kMaxNodesPerPass;  // [2][64] doubles as 2 words each (see PointwiseArgs::done_flag)
 constexpr int kXchgMaxRanks = 16;    // ranks in one peer-exchange group (one NVSwitch domain)
 constexpr int kXchgRec = 2 * kMaxNodesPerPass + 16;  // doubles per (slot, rank) record: S[64], Q[64], flag, pad
 constexpr int kXchgSlots = 2;        // records are double-buffered by call parity
@@ -42,8 +43,10 @@ struct PointwiseArgs {
     unsigned long long item_rows;           // rows per item (1: every row is an item)
     unsigned int rows_per_cta;
     unsigned int B, theta_len, K;
-    // host path: `out` is mapped pinned host memory; the last CTA publishes done_seq in *done_flag after the
-    // results (system-scope fence), and the host polls the flag instead of copying + synchronising
+    // host path (done_flag != nullptr): `out` is mapped pinned host memory and the results are delivered as
+    // self-validating words -- every double travels as two 8-byte stores {seq32 | low half}, {seq32 | high half}
+    // (aligned 8-byte stores are atomic over PCIe) -- so the kernel needs neither a system-scope fence nor a
+    // completion flag after them, and the host, polling the words, has each value as soon as it lands
     unsigned long long* done_flag;
     unsigned long long done_seq;
     PeerXchg xchg;
@@ -106,7 +109,7 @@ struct Engine {
     unsigned int* d_ticket = nullptr;
     double* h_theta = nullptr;   // pinned + mapped staging
     double* d_htheta = nullptr;  // device alias of h_theta
-    double* h_out = nullptr;     // pinned + mapped: [2][64] results, then the completion flag
+    double* h_out = nullptr;     // pinned + mapped: kHostOutWords self-validating result words, then the status word
     double* d_hout = nullptr;    // device alias of h_out
     unsigned long long host_seq = 0;
     unsigned long long* done_flag = nullptr;  // per launch: device alias of the flag, or nullptr

@@ -470,18 +470,17 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         if ((unsigned) tid < Bout) {
             if constexpr (BOLTZ) {
                 const double lp = -S * a.inv_temperature;  // one item: the whole energy
-                a.out[tid] = lp;
-                a.out[Bout + tid] = lp * lp;
+                S = lp;
+                Q = lp * lp;
+            }
+            if (a.done_flag) {  // host path: self-validating words into mapped host memory, no fence, no flag
+                store_result_words(a.out, tid, S, a.done_seq);
+                store_result_words(a.out, Bout + tid, Q, a.done_seq);
             } else {
                 a.out[tid] = S;
                 a.out[Bout + tid] = Q;
             }
         }
-    }
-    if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
-        if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
-        named_bar_sync(1, MV_CONSUMERS);
-        if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
     }
     if (tid == 0) *a.ticket = 0u;
     trace_mark(a.trace, 1, 2, tid == 0);

@@ -733,14 +733,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             if (a.xchg.gather_per) Bout = a.xchg.gather_total;
         }
         if ((unsigned) tid < Bout) {
-            a.out[tid] = S;
-            a.out[Bout + tid] = Q;
+            if (a.done_flag) {  // host path: self-validating words into mapped host memory, no fence, no flag
+                store_result_words(a.out, tid, S, a.done_seq);
+                store_result_words(a.out, Bout + tid, Q, a.done_seq);
+            } else {
+                a.out[tid] = S;
+                a.out[Bout + tid] = Q;
+            }
         }
-    }
-    if (a.done_flag) {  // host path: results went to mapped host memory; make them visible, then the flag
-        if ((unsigned) tid < kMaxNodesPerPass) __threadfence_system();
-        named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
-        if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
     }
     if (tid == 0) *a.ticket = 0u;  // ready for the next launch on this stream
     trace_mark(a.trace, 1, 2, tid == 0);
