@@ -215,14 +215,26 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                 st[u] = -1.0;
             }
         }
+        // a cut item ends in CTA cu when st >= 0: its total is tail(cs) + head(cs + 1) + ... + head(cu).  The two loads
+        // every stitch needs (tail of the first CTA, head of the last) are issued for the whole batch before any use;
+        // CTAs in between exist only when an item spans more than two CTAs.
+        double tl[BATCH], hd[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const bool stitch = stitching && st[u] >= 0.0;
+            const unsigned cu = c + u * NW, cs = stitch ? (unsigned) st[u] : 0u;
+            tl[u] = stitch ? ld_cg_f64(part + (size_t) cs * REC + 3 * kMaxNodesPerPass + bb) : 0.0;
+            hd[u] = stitch ? ld_cg_f64(part + (size_t) cu * REC + 2 * kMaxNodesPerPass + bb) : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
             S += s[u];
             Q += q[u];
-            if (st[u] >= 0.0) {  // a cut item ends in CTA cu: stitch it
+            if (stitching && st[u] >= 0.0) {
                 const unsigned cu = c + u * NW, cs = (unsigned) st[u];
-                double tot = ld_cg_f64(part + (size_t) cs * REC + 3 * kMaxNodesPerPass + bb);
-                for (unsigned k = cs + 1; k <= cu; ++k) tot += ld_cg_f64(part + (size_t) k * REC + 2 * kMaxNodesPerPass + bb);
+                double tot = tl[u];
+                for (unsigned k = cs + 1; k < cu; ++k) tot += ld_cg_f64(part + (size_t) k * REC + 2 * kMaxNodesPerPass + bb);
+                tot += hd[u];
                 S += tot;
                 Q = fma(tot, tot, Q);
             }

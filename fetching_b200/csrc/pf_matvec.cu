@@ -125,11 +125,13 @@ struct UnitIter {
     }
 };
 
-template <typename T, int RPL, bool BOLTZ, int NBK>
+template <typename T, int RPL, bool BOLTZ, int NBK, int MB = 4>
 __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid_constant__ MatvecArgs a) {
     using CT = typename std::conditional<sizeof(T) == 4, float, double>::type;
-    constexpr bool MMA = NBK > 0;  // tensor variant: NBK blocks of 8 nodes per warp, 4 blocks of 8 rows per warp
-    constexpr int MB = 4;
+    // tensor variant: NBK blocks of 8 nodes and MB blocks of 8 rows per warp (tile = 64 MB rows).  MB = 4 for the
+    // lasso; the small dense Boltzmann matrix takes MB = 1: its epilogue (one x_i load per row x node) is repeated
+    // for every column split, so short tiles x few splits make it 4x cheaper (3.9 -> ~1 us of a 16 us call)
+    constexpr bool MMA = NBK > 0;
     static_assert(!MMA || sizeof(T) == 8, "DMMA is the FP64 path");
     constexpr int KPV = 16 / (int) sizeof(T);             // k values per 16-byte vector
     constexpr int KCH = MV_CHUNK_BYTES / (int) sizeof(T);  // k values per chunk
@@ -537,9 +539,9 @@ int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
     return 0;
 }
 
-template <typename T, int RPL, bool BOLTZ, int NBK = 0>
+template <typename T, int RPL, bool BOLTZ, int NBK = 0, int MB = 4>
 int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
-    auto kern = mv_frontier_kernel<T, RPL, BOLTZ, NBK>;
+    auto kern = mv_frontier_kernel<T, RPL, BOLTZ, NBK, MB>;
     static bool configured_dev[64] = {};
     if (!configured_dev[e.device & 63]) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMvSmem);
@@ -619,13 +621,13 @@ int dispatch_rpl(Engine& e, MatvecArgs& a, unsigned rpl, cudaStream_t s) {
     }
 }
 
-template <bool BOLTZ>
+template <bool BOLTZ, int MB>
 int dispatch_mma(Engine& e, MatvecArgs& a, unsigned nbk, cudaStream_t s) {
     switch (nbk) {
-        case 1: return launch_mv<double, 1, BOLTZ, 1>(e, a, s);
-        case 2: return launch_mv<double, 1, BOLTZ, 2>(e, a, s);
-        case 4: return launch_mv<double, 1, BOLTZ, 4>(e, a, s);
-        default: return launch_mv<double, 1, BOLTZ, 8>(e, a, s);
+        case 1: return launch_mv<double, 1, BOLTZ, 1, MB>(e, a, s);
+        case 2: return launch_mv<double, 1, BOLTZ, 2, MB>(e, a, s);
+        case 4: return launch_mv<double, 1, BOLTZ, 4, MB>(e, a, s);
+        default: return launch_mv<double, 1, BOLTZ, 8, MB>(e, a, s);
     }
 }
 
@@ -639,7 +641,9 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     while (NG * MV_NODES_PER_LANE < B) NG *= 2;  // 1, 2, 4, 8
     const unsigned rpl = NG == 1 ? 1 : (NG == 2 ? 2 : 4);
     const bool mma = !e.f32 && e.mv_tensor;  // FP64: the contraction runs on the tensor cores (DMMA)
-    a.tile_rows = mma ? 256 : (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // 256, 256, 256, 128
+    // short tiles for a Boltzmann matrix whose 64-row tiles do not outnumber the SMs (see mv_frontier_kernel)
+    const bool short_tiles = mma && boltz && (e.n_rows + 63) / 64 <= (uint64_t) e.sm_count;
+    a.tile_rows = mma ? (short_tiles ? 64 : 256) : (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // vector: 256, 256, 256, 128
     a.B = B;
     a.Bpad = NG * MV_NODES_PER_LANE;
     a.theta = d_theta;
@@ -690,7 +694,8 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     }
     int r;
     if (mma)
-        r = boltz ? dispatch_mma<true>(e, a, NG, s) : dispatch_mma<false>(e, a, NG, s);
+        r = boltz ? (short_tiles ? dispatch_mma<true, 1>(e, a, NG, s) : dispatch_mma<true, 4>(e, a, NG, s))
+                  : dispatch_mma<false, 4>(e, a, NG, s);
     else if (boltz)
         r = e.f32 ? dispatch_rpl<float, true>(e, a, rpl, s) : dispatch_rpl<double, true>(e, a, rpl, s);
     else
