@@ -441,15 +441,20 @@ def main():
         chain_kw.update(dimension=prm["D"])
     def chain_run(**kw):
         barrier()
-        r = pf_chain.run_chain(eng, **chain_kw, **kw)
+        r = pf_chain.run_chain(eng, **chain_kw, collect_rows=False, **kw)
         torch.cuda.synchronize()
         return {"steps_per_sec": r.chain_steps_per_sec, "levels": int(r.stats["levels"]),
                 "engine_calls": int(r.stats["engine_calls"]), "node_passes": int(r.stats["nodes_scored"]),
                 "node_item_evals": int(r.stats["items_scored"]), "dropped_early": int(r.stats["abandoned"]),
-                "frontier": B, "accept_rate": float(r.accept[1:].mean()) if len(r.accept) > 1 else None,
+                "frontier": B, "accept_rate": float(r.stats["accepted"]) / max(1, int(r.stats["levels"]) - 1),
                 "seconds": r.stats["seconds"], "eval_seconds": r.stats["eval_seconds"]}
 
     chain_info = chain_run()  # nodes scored whole: one kernel pass per scheduling burst
+    if world == 1 and chain_info["seconds"] < 0.05:
+        # a 50-level chain of a small model lasts a few ms, most of it start-up: lengthen it to ~0.2 s
+        # (single process only: the length must be identical on every rank of a sharded run)
+        chain_kw["chain_length"] = int(min(5000, args.chain_length * 0.2 / max(chain_info["seconds"], 1e-4)))
+        chain_info = chain_run()
     n_items = eng.data_size * world if kind in ("mixture", "blasso") and world > 1 else eng.data_size
     if eng.data_size >= 16 and world == 1:
         # predictive mode (the reference's -b / -y 0): a probe batch of 1/16 of the items, then the rest,

@@ -51,7 +51,7 @@ class ChainStats(C.Structure):
         ("levels", C.c_uint64), ("rows", C.c_uint64), ("engine_calls", C.c_uint64), ("nodes_scored", C.c_uint64),
         ("max_frontier", C.c_uint64), ("allocated_nodes", C.c_uint64), ("recycled_nodes", C.c_uint64),
         ("seconds", C.c_double), ("eval_seconds", C.c_double), ("items_scored", C.c_uint64),
-        ("abandoned", C.c_uint64),
+        ("abandoned", C.c_uint64), ("accepted", C.c_uint64),
     ]
 
 

@@ -78,12 +78,16 @@ def run_chain(engine, chain_length: int = 100, frontier: int = 8, *, policy: int
               reassign_ratio: float = 1.1, dimension: int = 1, threshold: bool = False, verbose: bool = False,
               print_tsv: bool = False, seed: int = 0, tau: float = 5.0, initial_theta=None,
               trace_jobs: bool = False, deferred_proposals: bool = False, batch_items: int = 0,
-              update_style: int = 1) -> ChainResult:
+              update_style: int = 1, collect_rows: bool = True) -> ChainResult:
     """Defaults follow tree.cc:45-48 (-l 100 -r 1.1 -c 0.99 -d 1 -s 2).  batch_items > 0 turns on partial
-    updates (the reference's -b / -y), i.e. predictive scheduling from partial sums."""
+    updates (the reference's -b / -y), i.e. predictive scheduling from partial sums.  collect_rows = False passes
+    no row callback (a Python callback costs ~25 us per chain level, more than a small model's kernel pass):
+    timing runs use it and read the acceptance count from the stats."""
     cfg, _keep = _config(frontier, chain_length, policy, correlation, reassign_ratio, dimension, threshold, verbose,
                          print_tsv, seed, tau, initial_theta, deferred_proposals, batch_items, update_style)
     rows, jobs, row_cb, job_cb = _collect(trace_jobs)
+    if not collect_rows:
+        row_cb = ROW_FN()
     st = ChainStats()
     check(_lib.load().pf_chain_run(engine._h, C.byref(cfg), row_cb, job_cb, None, C.byref(st)), "pf_chain_run")
     return _result(rows, jobs, st)

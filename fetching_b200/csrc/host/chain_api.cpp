@@ -48,8 +48,10 @@ class ChainHook : public SamplerType {
             fn_(user_, depth, accept ? 1 : 0, metric_sum, buf_.data(), theta_len_);
         }
         ++rows_;
+        if (depth >= 1 && accept) ++accepted_;
     }
     std::size_t rows() const { return rows_; }
+    std::size_t accepted() const { return accepted_; }
 
   private:
     const Executor& ex_;
@@ -58,7 +60,7 @@ class ChainHook : public SamplerType {
     void* user_;
     bool print_;
     std::vector<double> buf_;
-    std::size_t rows_ = 0;
+    std::size_t rows_ = 0, accepted_ = 0;
 };
 
 struct JobTrace {
@@ -164,6 +166,7 @@ static int run_chain(const ChainTarget& tg, Executor& ex, const pf_chain_config&
         stats->rows = hook.rows();
         stats->items_scored = comm.stats().items_scored;
         stats->abandoned = comm.stats().abandoned + comm.stats().skipped;
+        stats->accepted = hook.accepted();
     }
     return eval.status;
 }

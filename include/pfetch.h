@@ -211,6 +211,7 @@ typedef struct pf_chain_stats {
     double seconds, eval_seconds;
     uint64_t items_scored;  /* sum over engine calls of nodes x items: the work paid for */
     uint64_t abandoned;     /* nodes dropped before completion (ABANDON, or found dead) */
+    uint64_t accepted;      /* accepted proposals among levels 1.. (the chain's acceptance count) */
 } pf_chain_stats;
 
 typedef void (*pf_chain_row_fn)(void* user, uint64_t depth, int accept, double metric_sum, const double* theta,
