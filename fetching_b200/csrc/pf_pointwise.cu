@@ -595,9 +595,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         const unsigned nrows = (unsigned) (t1 - t0);
         // rows in flight per lane: batches of RB rows with every shared-memory load issued before the first use
         // and no exit inside a batch (the one-row-per-item models are short dependent chains behind a 30-cycle LDS)
-        constexpr unsigned RB = M::ITEM1 ? 4 : 1;
+        // (mixture: several rows per iteration amortise the loop's re-materialised constants and overlap one row's
+        // serial log chain with the other rows' exps.  N = 1e8, B = 8: 6.51 ms with one row, 6.14 with two, 5.93 with
+        // four; with one node and 32 point-lanes (B = 1) a lane has only four rows of a tile and two at a time are
+        // best; with two nodes per lane batching only spills.)
         unsigned j = slot;
-        if constexpr (RB > 1) {
+        [[maybe_unused]] unsigned redo = 0u;  // slow_path_accumulate() key, tested once per tile
+        auto batch_rows = [&](auto rb_tag) {
+            constexpr unsigned RB = decltype(rb_tag)::value;
             for (; j + (RB - 1) * nslots < nrows; j += RB * nslots) {
                 CT x[RB][DIM];
 #pragma unroll
@@ -606,13 +611,22 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 for (unsigned u = 0; u < RB; ++u)
 #pragma unroll
                     for (int n = 0; n < NPL; ++n) {
-                        const double v = (double) M::rowlp(nd[n], x[u]);
+                        double v;
+                        if constexpr (M::HAS_REDO)
+                            v = (double) M::rowlp_fast(nd[n], x[u], redo);
+                        else
+                            v = (double) M::rowlp(nd[n], x[u]);
                         accS[n] += v;
                         if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
                     }
             }
+        };
+        if constexpr (M::ITEM1)
+            batch_rows(std::integral_constant<unsigned, 4>{});
+        else if constexpr (NPL == 1) {
+            if (PL <= 8) batch_rows(std::integral_constant<unsigned, 4>{});
+            batch_rows(std::integral_constant<unsigned, 2>{});
         }
-        [[maybe_unused]] unsigned redo = 0u;  // slow_path_accumulate() key, tested once per tile
         for (; j < nrows; j += nslots) {
             CT x[DIM];
             load_row<T, DIM, CT>(base + (size_t) j * RB_BYTES, x);
