@@ -52,6 +52,8 @@ struct PointwiseArgs {
     PeerXchg xchg;
     // host path, small frontiers: the thetas travel INSIDE the kernel parameters (constant bank, broadcast to every
     // CTA) instead of through a host->device copy in front of the kernel (~8 us of a ~27 us call)
+    unsigned int out_off, out_stride;     // results go to out[out_off + b] and out[out_stride + out_off + b]
+                                          // (out_stride 0: the launch's own node count) -- a frontier scored in two launches
     unsigned long long* trace;            // diagnostics (PF_TRACE=1): %globaltimer marks of CTA 0 [0..15] and of the
                                           // finalizing CTA [16..31]; nullptr in normal operation
     unsigned int theta_inline_n;          // doubles valid in theta_inline; 0: read `theta`

@@ -747,12 +747,13 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             if (a.xchg.gather_per) Bout = a.xchg.gather_total;
         }
         if ((unsigned) tid < Bout) {
+            const unsigned iS = a.out_off + tid, iQ = (a.out_stride ? a.out_stride : Bout) + a.out_off + tid;
             if (a.done_flag) {  // host path: self-validating words into mapped host memory, no fence, no flag
-                store_result_words(a.out, tid, S, a.done_seq);
-                store_result_words(a.out, Bout + tid, Q, a.done_seq);
+                store_result_words(a.out, iS, S, a.done_seq);
+                store_result_words(a.out, iQ, Q, a.done_seq);
             } else {
-                a.out[tid] = S;
-                a.out[Bout + tid] = Q;
+                a.out[iS] = S;
+                a.out[iQ] = Q;
             }
         }
     }
@@ -1057,6 +1058,31 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
         // normalsampler.hh:73-75).
         const bool general = e.normal_general;
         return e.f32 ? dispatch_normal<float>(e, a, s, general) : dispatch_normal<double>(e, a, s, general);
+    }
+    if (!e.f32 && B > 32 && a.xchg.gather_per == 0) {
+        // FP64 mixture, more than 32 nodes: two launches of <= 32 nodes (one node per lane) beat one launch with two
+        // nodes per lane, which runs out of registers (N = 1e8, B = 64: 45.5 vs 52.7 ms); the data set is read twice,
+        // which an FP64-bound kernel does not notice.  Each launch makes its own peer exchange.
+        PointwiseArgs lo = a, hi = a;
+        lo.B = 32;
+        lo.out_off = 0;
+        lo.out_stride = B;
+        lo.theta_inline_n = 0;
+        hi.B = B - 32;
+        hi.theta = d_theta + (size_t) 32 * e.theta_len;
+        hi.out_off = 32;
+        hi.out_stride = B;
+        hi.theta_inline_n = 0;
+        if (a.theta_inline_n) {  // (tiny thetas only) the inline copy holds all B nodes: re-slice it
+            lo.theta_inline_n = 32 * e.theta_len;
+            hi.theta_inline_n = (B - 32) * e.theta_len;
+            memcpy(hi.theta_inline, a.theta_inline + (size_t) 32 * e.theta_len, (size_t) hi.theta_inline_n * sizeof(double));
+        }
+        const int r1 = dispatch_mixture<double>(e, lo, s);
+        if (r1 < 0) return r1;
+        hi.xchg = e.next_xchg();
+        const int r2 = dispatch_mixture<double>(e, hi, s);
+        return r2 < 0 ? r2 : r1 + r2;
     }
     return e.f32 ? dispatch_mixture<float>(e, a, s) : dispatch_mixture<double>(e, a, s);
 }

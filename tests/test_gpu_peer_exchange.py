@@ -67,7 +67,8 @@ def test_mixture_row_shards_exchange(fb, G, B):
         launches0 = [e.launch_count for e in engs]
         res = run_ranks(engs, thetas, calls=3)  # three calls: both slots and a slot reuse
         for e, l0 in zip(engs, launches0):
-            assert e.launch_count - l0 == 3  # one kernel per call: no collective kernel behind it
+            # one kernel per call (two for a mixture frontier of more than 32 nodes): no collective kernel behind it
+            assert e.launch_count - l0 == 3 * (2 if B > 32 else 1)
             e.peer_status()
         for s, q in res:
             assert rel(s, fs) < 1e-12 and rel(q, fq) < 1e-12
