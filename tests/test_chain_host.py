@@ -141,3 +141,17 @@ def test_predictive_partial_evaluation_saves_work_and_keeps_the_chain(orc):
     assert whole.stats["items_scored"] == whole.stats["nodes_scored"] * 10000
     assert part.stats["items_scored"] < 0.5 * whole.stats["items_scored"]
     assert part.stats["abandoned"] > 0
+
+
+def test_chain_stats_count_acceptances_without_a_row_callback(orc):
+    """Timing runs pass no row callback (collect_rows=False semantics of run_chain): the acceptance count must
+    then come from pf_chain_stats.accepted."""
+    from fetching_b200 import chain as pf_chain
+    data = orc.normal_dataset(2000)
+
+    def ev(th):
+        return orc.normal_frontier(data, th)
+
+    r = pf_chain.run_chain_with_evaluator(1, 2, 0, len(data), ev, chain_length=60, frontier=8)
+    assert int(r.stats["accepted"]) == int(r.accept[r.depth >= 1].sum())
+    assert int(r.stats["levels"]) >= 60
