@@ -1,5 +1,6 @@
 // pf_engine.cu -- the C ABI declared in include/pfetch.h: engine lifetime, data residency,
-// host- and device-pointer evaluation paths, NCCL all-reduce of the per-node partials.
+// host- and device-pointer evaluation paths, the multi-GPU set-up (peer exchange buffers over CUDA IPC for the
+// in-kernel exchange of the per-node partials; NCCL all-reduce / all-gather as the alternative).
 //
 // There is NO CPU fallback anywhere in this file: a missing sm_100 device is PF_ERR_NO_DEVICE.
 #include <dlfcn.h>

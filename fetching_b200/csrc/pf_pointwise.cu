@@ -660,7 +660,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         } else {
             // Tile total per node: lanes -> warp (shuffles) -> per-warp slot in one of 4 rotating
             // buffers.  Every warp ARRIVES on the tile's named barrier and moves on; only the owner
-            // warp(s) -- the ones holding threads tid < B -- WAIT on it, then fold the 7 slots.  The
+            // warp(s) -- the ones holding threads tid < B -- WAIT on it, then fold the per-warp slots.  The
             // smem stage is released after the arrival, which bounds any warp's lead to 3 tiles, so a
             // buffer is never rewritten before the owners have read it.
             double* r = red + (t & (PW_RED_BUFS - 1)) * (PW_CONSUMER_WARPS * kMaxNodesPerPass);

@@ -29,9 +29,9 @@
  *   pf_eval_frontier_range the same over items [first, first+count) -- the partial updates of
  *                          worker.hh:141-162 (batch_size items per MetricChange)
  *   pf_blasso_log_prior    python.cc:168-176 -> pyblasso.py:123-133
- *   pf_engine_comm_init    nothing (the reference has no data parallelism): row
- *                          shards of one data set on several GPUs, partial (sum, sum_sq)
- *                          all-reduced with NCCL over NVLink
+ *   pf_engine_peer_attach  nothing (the reference has no data parallelism): row
+ *   pf_engine_comm_init    shards of one data set on several GPUs, partial (sum, sum_sq) exchanged
+ *                          inside the frontier kernel over NVLink peer memory, or all-reduced with NCCL
  *
  * THETA LAYOUT (doubles per node = pf_engine_theta_len()):
  *   PF_MODEL_NORMAL           D means, then the packed lower-triangular covariance,
@@ -72,7 +72,7 @@ enum pf_status {
     PF_ERR_SHAPE = -3,        /* sizes inconsistent with the model */
     PF_ERR_NOMEM = -4,
     PF_ERR_UNSUPPORTED = -5,  /* e.g. dimension outside what the kernels are built for */
-    PF_ERR_NCCL = -6,
+    PF_ERR_NCCL = -6,         /* the exchange between GPUs failed (NCCL error, or a peer never arrived) */
     PF_ERR_NO_DEVICE = -7     /* no sm_100 device: there is NO CPU fallback */
 };
 
@@ -121,8 +121,11 @@ PF_API uint32_t pf_engine_dim(const pf_engine* e);
 PF_API uint32_t pf_engine_components(const pf_engine* e);
 
 /* Score B frontier nodes over ALL items.  thetas: HOST [B][theta_len]; sum, sum_sq: HOST [B]
- * (overwritten).  Host->device copy of thetas, kernels, optional all-reduce, device->host copy
- * of 2*B doubles, all on the engine's stream; returns when the results are in `sum`/`sum_sq`. */
+ * (overwritten).  The thetas reach the device in the kernel parameters (small frontiers of the pointwise
+ * models) or by a host->device copy on the engine's stream; the frontier kernel(s) -- including the exchange
+ * between GPUs when peers are attached -- deliver the 2*B results as self-validating words in mapped pinned
+ * memory, which this call polls: no device->host copy, no stream synchronise.  Returns when the results are
+ * in `sum` / `sum_sq`. */
 PF_API int pf_eval_frontier(pf_engine* e, uint32_t B, const double* thetas, double* sum, double* sum_sq);
 
 /* The same call `iters` times back to back (every iteration a complete pf_eval_frontier: theta from the host
