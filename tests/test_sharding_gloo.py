@@ -39,6 +39,55 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+class _FakeEngine:
+    """Stands in for FrontierEngine in the handle exchange of init_engine_peers (no GPU here)."""
+
+    def __init__(self, rank):
+        self.rank, self.attached = rank, None
+
+    def peer_export(self):
+        return bytes([self.rank]) * 64
+
+    def peer_attach(self, handles, rank, nranks):
+        self.attached = (list(handles), rank, nranks)
+
+
+def _peer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from fetching_b200 import distributed as pfd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(rank)
+    pfd.init_engine_peers(eng)
+    handles, r, n = eng.attached
+    ok = r == rank and n == world and len(handles) == world and all(h == bytes([k]) * 64 for k, h in enumerate(handles))
+    # the node-split bookkeeping the in-kernel gather relies on: output node b = record b // per, column b % per
+    for B in (3, 13, 64):
+        per = -(-B // world)
+        cuts = pfd.node_slices(B, world)
+        ok = ok and all(cuts[b // per][0] + b % per == b for b in range(B))
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_handles_reach_every_rank_in_rank_order(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world * 11 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r for r, _ in res] == list(range(world)) and all(ok for _, ok in res)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_row_shards_plus_allreduce_equal_single_shard(world):
     import torch.multiprocessing as mp
