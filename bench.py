@@ -300,6 +300,9 @@ def main():
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
                     help="N > 1: reduce the per-node partials inside the frontier kernel over NVLink peer memory "
                          "(default) or with ncclAllReduce after it")
+    ap.add_argument("--split", default="rows", choices=["rows", "nodes"],
+                    help="N > 1: rows = item-aligned row shards (large N); nodes = every GPU holds the whole (small) data "
+                         "set and scores ceil(B/N) nodes of the frontier (PF_OPT_NODE_SPLIT, in-kernel gather)")
     ap.add_argument("--chain-length", type=int, default=50, help="levels of the chain-steps/s measurement")
     args = ap.parse_args()
 
@@ -345,7 +348,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    shard = make_shard(kind, prm, rank, world)
+    node_split = world > 1 and args.split == "nodes"
+    shard = make_shard(kind, prm, 0, 1) if node_split else make_shard(kind, prm, rank, world)
     rows_local = shard["data"].shape[0]
     thetas = make_thetas(kind, prm, shard, B)
     eng = make_engine(kind, prm, shard, args.dtype, local_rank)
@@ -372,6 +376,11 @@ def main():
                     eng.set_option(fb.OPT_PEER_EXCHANGE, 0)
                 args.reduce = "nccl"
                 config["parallelism"] = "row-shard x%d + NCCL all-reduce of 2*B doubles" % world
+    if node_split:
+        assert args.reduce == "peer" and world <= B <= 64, "node split: peers attached and N <= B <= 64"
+        eng.set_option(fb.OPT_NODE_SPLIT, 1)
+        config["parallelism"] = "node split x%d (replicated data, %d nodes per GPU, in-kernel NVLink gather)" % (
+            world, -(-B // world))
     shard.pop("data")  # the engine owns the device copy; free the host rows
 
     # an explicit stream: handle 0 (the legacy default stream) means "the engine's own stream" in the C ABI
@@ -455,7 +464,7 @@ def main():
         # (single process only: the length must be identical on every rank of a sharded run)
         chain_kw["chain_length"] = int(min(5000, args.chain_length * 0.2 / max(chain_info["seconds"], 1e-4)))
         chain_info = chain_run()
-    n_items = eng.data_size * world if kind in ("mixture", "blasso") and world > 1 else eng.data_size
+    n_items = eng.data_size * world if kind in ("mixture", "blasso") and world > 1 and not node_split else eng.data_size
     if eng.data_size >= 16 and world == 1:
         # predictive mode (the reference's -b / -y 0): a probe batch of 1/16 of the items, then the rest,
         # only for the nodes the tree still believes in
@@ -463,7 +472,8 @@ def main():
 
     if rank == 0:
         pk, pk_src = peaks()
-        abytes = algorithmic_bytes(kind, prm, rows_local, B, args.dtype)
+        B_kernel = -(-B // world) if node_split else B  # nodes one GPU's kernel scores
+        abytes = algorithmic_bytes(kind, prm, rows_local, B_kernel, args.dtype)
         achieved = abytes / (kern_ms * 1e-3) / 1e9
         evals = B * K / (ms_total * 1e-3)
         line = {
@@ -483,7 +493,7 @@ def main():
                          "algorithmic_bytes_per_launch": int(abytes), "kernel_ms": kern_ms},
         }
         line["chain"] = chain_info
-        fp64 = fp64_view(kind, prm, rows_local, B, args.dtype, kern_ms, local_rank)
+        fp64 = fp64_view(kind, prm, rows_local, B_kernel, args.dtype, kern_ms, local_rank)
         if fp64:
             line["roofline"]["fp64_pipe"] = fp64
         if world == 1:
