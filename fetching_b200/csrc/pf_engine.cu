@@ -845,6 +845,11 @@ int pf_engine_peer_attach(pf_engine* pe, const void* handles, int rank, int nran
         return PF_ERR_INVALID;
     }
     Engine& e = *reinterpret_cast<Engine*>(pe);
+    if (e.peer_attached) {
+        // sequence numbers and the flags already sitting in the peers' buffers belong to the first attachment
+        pf::set_error("pf_engine_peer_attach: this engine already has its peers (create a new engine to regroup)");
+        return PF_ERR_INVALID;
+    }
     int r = peer_alloc(e);
     if (r != PF_OK) return r;
     if (cudaSetDevice(e.device) != cudaSuccess) return PF_ERR_CUDA;
@@ -862,6 +867,11 @@ int pf_engine_peer_attach(pf_engine* pe, const void* handles, int rank, int nran
         if (ce != cudaSuccess) {
             pf::set_error("cudaIpcOpenMemHandle(rank %d): %s", k, cudaGetErrorString(ce));
             cudaGetLastError();
+            for (int j = 0; j < k; ++j)  // leave nothing half-attached
+                if (e.peer_mapped[j]) {
+                    cudaIpcCloseMemHandle(e.peer_mapped[j]);
+                    e.peer_mapped[j] = nullptr;
+                }
             return PF_ERR_CUDA;
         }
         e.peer_mapped[k] = p;
@@ -876,6 +886,10 @@ int pf_engine_peer_attach_local(pf_engine* const* engines, int nranks) {
     for (int k = 0; k < nranks; ++k) {
         if (!engines[k]) return PF_ERR_INVALID;
         Engine& e = *reinterpret_cast<Engine*>(engines[k]);
+        if (e.peer_attached) {
+            pf::set_error("pf_engine_peer_attach_local: engine %d already has its peers", k);
+            return PF_ERR_INVALID;
+        }
         int r = peer_alloc(e);
         if (r != PF_OK) return r;
         table[k] = e.d_xchg;

@@ -168,7 +168,8 @@ PF_API int pf_engine_comm_init(pf_engine* e, const void* id128, int rank, int nr
  *                                rank / nranks like pf_engine_comm_init and selects the fused exchange
  *   pf_engine_peer_attach_local  all engines of the group live in THIS process (any devices): no IPC
  *   pf_engine_peer_status        PF_ERR_NCCL after a call in which some rank never arrived (20 s timeout)
- * Every rank must make the same sequence of evaluation calls (as with any collective). nranks <= 16. */
+ * Every rank must make the same sequence of evaluation calls (as with any collective). nranks <= 16.  An engine
+ * is attached once: regrouping means new engines. */
 PF_API int pf_engine_peer_export(pf_engine* e, void* handle64);
 PF_API int pf_engine_peer_attach(pf_engine* e, const void* handles, int rank, int nranks);
 PF_API int pf_engine_peer_attach_local(pf_engine* const* engines, int nranks);

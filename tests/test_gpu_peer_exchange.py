@@ -172,3 +172,12 @@ def test_exchange_option_needs_attachment(fb):
     with fb.FrontierEngine.mixture(data, 8, 1000) as e:
         with pytest.raises(fb.PfetchError):
             e.set_option(fb.OPT_PEER_EXCHANGE, 1)
+    # an engine joins a group once
+    engs = [fb.FrontierEngine.mixture(data, 8, 1000) for _ in range(2)]
+    try:
+        fb.peer_attach_local(engs)
+        with pytest.raises(fb.PfetchError):
+            fb.peer_attach_local(engs)
+    finally:
+        for e in engs:
+            e.close()
