@@ -50,7 +50,7 @@ class ReplayStream {
     static constexpr result_type max() { return Mt19937::max(); }
 
   private:
-    static constexpr std::size_t kKeep = 8192;  // outputs kept for cheap rewinds
+    static constexpr std::size_t kKeep = 65536;  // outputs kept for cheap rewinds (32 proposals of a 1000-dimensional model)
     void produce() {
         if (window_.size() >= 2 * kKeep) {
             window_.erase(window_.begin(), window_.begin() + kKeep);
