@@ -10,6 +10,7 @@
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -215,11 +216,21 @@ class BLassoExecutor {
         else {
             load_doubles(job.theta, theta_.data(), theta_.size());
             if (job.need_proposal()) {
-                BoxMullerNormal jump(0.0, std::sqrt(std::exp(job.scale)));
-                std::vector<double> next(theta_.size());
-                do {
-                    for (std::size_t i = 0; i < theta_.size(); ++i) next[i] = theta_[i] + jump(engine_);
-                } while (!(next[0] > 0.0));
+                // first attempt through the shared cache (the nodes of a depth draw at the same position, rng.hpp); a
+                // redraw (sigma <= 0, rare) continues the SAME distribution object, whose cached second variate of the
+                // last pair comes first when the vector length is odd: replay the attempt on a scalar distribution
+                const double sigma = std::sqrt(std::exp(job.scale));
+                const std::size_t n = theta_.size(), start = engine_.position();
+                std::vector<double> next(n), z(n);
+                normal_fill_cached(*noise_, engine_, 0.0, sigma, z.data(), n);
+                for (std::size_t i = 0; i < n; ++i) next[i] = theta_[i] + z[i];
+                if (!(next[0] > 0.0)) {
+                    engine_.set_position(start);
+                    BoxMullerNormal jump(0.0, sigma);
+                    do {
+                        for (std::size_t i = 0; i < n; ++i) next[i] = theta_[i] + jump(engine_);
+                    } while (!(next[0] > 0.0));
+                }
                 theta_.swap(next);
             }
         }
@@ -248,6 +259,7 @@ class BLassoExecutor {
     double tau_;
     std::vector<double> theta_, initial_;
     ReplayStream engine_;
+    std::shared_ptr<NoiseCache> noise_ = std::make_shared<NoiseCache>();  // shared by the copies (one per virtual worker)
 };
 
 // Dense Boltzmann (BASELINE config 2, new workload): state x in R^D, log p = -x'Wx/T, one item.
@@ -264,8 +276,9 @@ class BoltzmannDenseExecutor {
         else {
             load_doubles(job.theta, theta_.data(), theta_.size());
             if (job.need_proposal()) {
-                BoxMullerNormal step(0.0, 0.1);
-                for (double& v : theta_) v += step(engine_);
+                z_.resize(theta_.size());
+                normal_fill_cached(*noise_, engine_, 0.0, 0.1, z_.data(), z_.size());  // see NoiseCache (rng.hpp)
+                for (std::size_t i = 0; i < theta_.size(); ++i) theta_[i] += z_[i];
             }
         }
         return save_doubles(theta_.data(), theta_.size());
@@ -282,8 +295,9 @@ class BoltzmannDenseExecutor {
 
   private:
     int D_;
-    std::vector<double> theta_;
+    std::vector<double> theta_, z_;
     ReplayStream engine_;
+    std::shared_ptr<NoiseCache> noise_ = std::make_shared<NoiseCache>();  // shared by the copies (one per virtual worker)
 };
 
 } }  // namespace pf::host
