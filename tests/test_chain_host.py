@@ -155,3 +155,31 @@ def test_chain_stats_count_acceptances_without_a_row_callback(orc):
     r = pf_chain.run_chain_with_evaluator(1, 2, 0, len(data), ev, chain_length=60, frontier=8)
     assert int(r.stats["accepted"]) == int(r.accept[r.depth >= 1].sum())
     assert int(r.stats["levels"]) >= 60
+
+
+def test_shared_noise_and_stream_do_not_change_proposals(orc):
+    """Executors of the virtual workers share one replayable stream and, per stream position, one set of Box-Muller
+    products (host/rng.hpp: ReplayStream, NoiseCache).  With a frontier of 1 every position is visited by a single
+    node (the cache never hits), with a wide frontier most nodes are served from it: the chains must be identical,
+    also through the lasso's redraw path (sigma <= 0 -> draw again from the SAME distribution object, odd length)."""
+    from fetching_b200 import _lib, chain, models
+    D = 301
+    W, _ = models.boltzmann_dataset(D, 4, seed=2)
+    ev = lambda th: orc.boltzmann_dense_frontier(W, th, 1.0)
+    runs = [chain.run_chain_with_evaluator(_lib.MODEL_BOLTZMANN_DENSE, D, 0, 1, ev, chain_length=40, frontier=f,
+                                           dimension=D, deferred_proposals=d) for f, d in ((1, False), (64, False), (8, True))]
+    for r in runs[1:]:
+        assert np.array_equal(runs[0].theta, r.theta) and np.array_equal(runs[0].accept, r.accept)
+        assert np.array_equal(runs[0].metric_sum, r.metric_sum)
+    # the scalar distribution gives the same values as the cached products: first proposal of the chain by hand
+    step = runs[0].theta[1] - runs[0].theta[0] if runs[0].accept[1] else None
+    assert runs[0].theta.shape[1] == D and (step is None or np.all(np.abs(step) < 1.0))
+
+    p = 40  # theta has 41 values (odd); sigma starts tiny, so proposals with sigma <= 0 and redraws are frequent
+    X, y, beta = models.blasso_dataset(2000, p, seed=4)
+    ev = lambda th: orc.blasso_frontier(X, y, th, 500)
+    init = np.concatenate([[1e-3], beta])
+    runs = [chain.run_chain_with_evaluator(_lib.MODEL_BLASSO, p, 0, 4, ev, chain_length=40, frontier=f, dimension=p + 1,
+                                           initial_theta=init) for f in (1, 16)]
+    assert np.array_equal(runs[0].theta, runs[1].theta) and np.array_equal(runs[0].accept, runs[1].accept)
+    assert np.all(runs[0].theta[:, 0] > 0)
