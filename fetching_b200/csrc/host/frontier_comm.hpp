@@ -132,20 +132,20 @@ class FrontierCommunicator {
         setup_job(executors_[rank], job, proposal);
         proposal.proposal_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (trace_) trace_->job(job_in, proposal);
-        if (job_in.state != JobInfoT::s_has_proposal) {
-            if (eager_) tree_.set_proposal(proposal, rank);
-            proposals_[rank].push_back(proposal);
-            push(rank, FC_SETPROPOSAL);
-        }
         FrontierJob fj{rank, job.id, job.generation, proposal.proposal};
         order_of(executors_[rank], fj, 0);
+        if (job_in.state != JobInfoT::s_has_proposal) {
+            if (eager_) tree_.set_proposal(proposal, rank);
+            proposals_[rank].push_back(std::move(proposal));  // (theta is kilobytes for the big models: move, not copy)
+            push(rank, FC_SETPROPOSAL);
+        }
         ++stats_.jobs;
         if (batch_items_ == 0)
-            batch_.push_back(fj);
+            batch_.push_back(std::move(fj));
         else {  // worker.hh:130-135: cumulative sums continue from what the tree already has
             Work& w = work_[rank];
             w.active = true;
-            w.job = fj;
+            w.job = std::move(fj);
             w.position = job_in.first_position;
             w.sum = job_in.metric_sum;
             w.sum_sq = job_in.metric_sum_sq;
