@@ -12,6 +12,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PFETCH_LIB") or os.path.join(PKG, "lib", "libpfetch.so")  # PFETCH_LIB: experimental variants
 
 PF_OK = 0
+PF_ERR_INVALID, PF_ERR_CUDA, PF_ERR_SHAPE, PF_ERR_NOMEM, PF_ERR_UNSUPPORTED, PF_ERR_NCCL, PF_ERR_NO_DEVICE = (
+    -1, -2, -3, -4, -5, -6, -7)
 STATUS = {0: "PF_OK", -1: "PF_ERR_INVALID", -2: "PF_ERR_CUDA", -3: "PF_ERR_SHAPE", -4: "PF_ERR_NOMEM",
           -5: "PF_ERR_UNSUPPORTED", -6: "PF_ERR_NCCL", -7: "PF_ERR_NO_DEVICE"}
 
@@ -72,6 +74,7 @@ SYMBOLS = {
     "pf_engine_model": (C.c_int, [C.c_void_p]),
     "pf_engine_dim": (C.c_uint32, [C.c_void_p]),
     "pf_engine_components": (C.c_uint32, [C.c_void_p]),
+    "pf_engine_group": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pf_chain_run": (C.c_int, [C.c_void_p, C.POINTER(ChainConfig), ROW_FN, JOB_FN, C.c_void_p,
                                C.POINTER(ChainStats)]),
     "pf_chain_run_with_evaluator": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(ChainConfig),

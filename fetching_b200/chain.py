@@ -25,6 +25,7 @@ class ChainResult:
     theta: np.ndarray          # [rows][theta_len]
     stats: dict
     jobs: List[tuple] = field(default_factory=list)  # (id, generation, state, path, rp, prop_rp, next_rp, log_prior, theta)
+    status: int = 0            # pf_status of the run (only ever non-zero with check_status=False)
 
     @property
     def chain_steps_per_sec(self) -> float:
@@ -99,9 +100,11 @@ def run_chain_with_evaluator(model: int, dim: int, components: int, data_size: i
                              dimension: int = 1, threshold: bool = False, verbose: bool = False, seed: int = 0,
                              tau: float = 5.0, initial_theta=None, trace_jobs: bool = False,
                              deferred_proposals: bool = False, batch_items: int = 0, update_style: int = 1,
-                             range_evaluator=None) -> ChainResult:
+                             range_evaluator=None, check_status: bool = True) -> ChainResult:
     """Same tree / sampler / hand-off, frontier scored by `evaluator(thetas[B][L]) -> (sum[B], sum_sq[B])`.
-    No GPU involved: used to exercise the host logic (the CPU test-suite passes the oracle here)."""
+    No GPU involved: used to exercise the host logic (the CPU test-suite passes the oracle here).
+    An evaluator may return an int instead: a negative pf_status, i.e. a failed engine call -- the chain must stop
+    there (check_status=False returns the rows delivered so far with `.status` instead of raising)."""
     cfg, _keep = _config(frontier, chain_length, policy, correlation, reassign_ratio, dimension, threshold, verbose,
                          False, seed, tau, initial_theta, deferred_proposals, batch_items, update_style)
     rows, jobs, row_cb, job_cb = _collect(trace_jobs)
@@ -109,7 +112,10 @@ def run_chain_with_evaluator(model: int, dim: int, components: int, data_size: i
 
     def on_eval(_u, B, thetas, s_out, q_out):
         th = np.ctypeslib.as_array(thetas, shape=(B, theta_len))
-        s, q = evaluator(th)
+        r = evaluator(th)
+        if isinstance(r, int):
+            return r
+        s, q = r
         np.ctypeslib.as_array(s_out, shape=(B,))[:] = s
         np.ctypeslib.as_array(q_out, shape=(B,))[:] = q
         return 0
@@ -117,14 +123,20 @@ def run_chain_with_evaluator(model: int, dim: int, components: int, data_size: i
     def on_range(_u, B, thetas, first, count, order, s_out, q_out):
         th = np.ctypeslib.as_array(thetas, shape=(B, theta_len))
         od = np.ctypeslib.as_array(order, shape=(B, 2))
-        s, q = range_evaluator(th, int(first), int(count), od)
+        r = range_evaluator(th, int(first), int(count), od)
+        if isinstance(r, int):
+            return r
+        s, q = r
         np.ctypeslib.as_array(s_out, shape=(B,))[:] = s
         np.ctypeslib.as_array(q_out, shape=(B,))[:] = q
         return 0
 
     st = ChainStats()
     range_cb = RANGE_FN(on_range) if range_evaluator is not None else RANGE_FN()
-    check(_lib.load().pf_chain_run_with_evaluator(model, dim, components, data_size, C.byref(cfg), EVAL_FN(on_eval),
-                                                  range_cb, None, row_cb, job_cb, None, C.byref(st)),
-          "pf_chain_run_with_evaluator")
-    return _result(rows, jobs, st)
+    rc = _lib.load().pf_chain_run_with_evaluator(model, dim, components, data_size, C.byref(cfg), EVAL_FN(on_eval),
+                                                 range_cb, None, row_cb, job_cb, None, C.byref(st))
+    if check_status:
+        check(rc, "pf_chain_run_with_evaluator")
+    res = _result(rows, jobs, st)
+    res.status = int(rc)
+    return res

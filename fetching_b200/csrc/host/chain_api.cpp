@@ -18,6 +18,10 @@
 #include "sampler_type.hpp"
 #include "spec_tree.hpp"
 
+namespace pf {
+void set_error(const char* fmt, ...);  // pf_engine.cu: the text behind pf_last_error()
+}
+
 namespace pf { namespace host {
 
 struct HostTypes {
@@ -84,6 +88,12 @@ struct FrontierEvaluator {
     void* user;
     uint32_t theta_len;
     int status = PF_OK;
+    // Row-sharded engine group (pf_engine_peer_attach / pf_engine_comm_init): every rank holds `shards` times fewer
+    // items than the chain sees.  The tree's item j is local item j / shards of rank j % shards, so a range of the
+    // chain's items that starts and ends at multiples of `shards` is the same LOCAL range on every rank, and the
+    // exchange inside the engine adds the ranks' partial sums.
+    std::size_t shards = 1;
+    bool failed() const { return status != PF_OK; }
     std::vector<double> thetas;
     void operator()(const std::vector<FrontierJob>& jobs, std::vector<double>& sum, std::vector<double>& sum_sq) {
         thetas.assign(jobs.size() * (std::size_t) theta_len, 0.0);
@@ -105,7 +115,7 @@ struct FrontierEvaluator {
         }
         int r;
         if (engine)
-            r = pf_eval_frontier_range(engine, (uint32_t) jobs.size(), thetas.data(), first, count,
+            r = pf_eval_frontier_range(engine, (uint32_t) jobs.size(), thetas.data(), first / shards, count / shards,
                                        ordered ? order.data() : nullptr, sum.data(), sum_sq.data());
         else
             r = range_fn ? range_fn(user, (uint32_t) jobs.size(), thetas.data(), first, count, order.data(), sum.data(),
@@ -126,6 +136,7 @@ struct ChainTarget {  // what is being sampled and who scores it
     pf_chain_eval_fn fn;
     void* eval_user;
     pf_chain_range_fn range_fn;
+    std::size_t shards = 1;  // ranks of a row-sharded engine group (1: the engine holds the whole data set)
 };
 
 template <class Executor>
@@ -143,12 +154,14 @@ static int run_chain(const ChainTarget& tg, Executor& ex, const pf_chain_config&
     if (cfg.print_tsv) hook.SamplerType::notify(tree, 0, 0, std::string(), false);  // the header line
 
     FrontierEvaluator eval{tg.engine, tg.fn, tg.eval_user, theta_len};
+    eval.shards = tg.shards;
     eval.range_fn = tg.range_fn;
     eval.ordered = tg.model == PF_MODEL_NORMAL;
     JobTrace trace{job, user, theta_len, {}};
     FrontierCommunicator<SpecTree, Executor, HostTypes, FrontierEvaluator, JobTrace> comm(
-        tree, ex, eval, workers, data_size, &trace, cfg.deferred_proposals == 0, (std::size_t) cfg.batch_items,
-        (int) cfg.update_style);
+        tree, ex, eval, workers, data_size, &trace, cfg.deferred_proposals == 0,
+        // partial updates of a sharded group cover whole rounds of the shards (see FrontierEvaluator::shards)
+        ((std::size_t) cfg.batch_items + tg.shards - 1) / tg.shards * tg.shards, (int) cfg.update_style);
     SpecTree::run_behavior rb;
     rb.quiet = cfg.verbose == 0;
     const auto t0 = std::chrono::steady_clock::now();
@@ -208,6 +221,19 @@ extern "C" PF_API int pf_chain_run(pf_engine* engine, const pf_chain_config* cfg
     pf::host::ChainTarget tg{pf_engine_model(engine), pf_engine_dim(engine), pf_engine_components(engine),
                              pf_engine_theta_len(engine), (std::size_t) pf_engine_data_size(engine), engine, nullptr,
                              nullptr, nullptr};
+    int rank = 0, nranks = 1, node_split = 0;
+    pf_engine_group(engine, &rank, &nranks, &node_split);
+    if (nranks > 1 && !node_split) {
+        // Row shards: the chain samples the posterior of the WHOLE data set, so it sees nranks x the local item count
+        // (every rank must hold the same number of items -- pfetch.h -- or the ranks' trees would diverge).
+        if (tg.model == PF_MODEL_NORMAL && cfg->batch_items) {
+            pf::set_error("pf_chain_run: StrideIndex-ordered partial ranges address the whole data set; not available "
+                                 "on a row shard (use batch_items = 0)");
+            return PF_ERR_UNSUPPORTED;
+        }
+        tg.shards = (std::size_t) nranks;
+        tg.data_size *= (std::size_t) nranks;
+    }
     return dispatch_chain(tg, cfg, row, job, user, stats);
 }
 

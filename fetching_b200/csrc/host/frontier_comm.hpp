@@ -17,7 +17,12 @@
 // evidence (master.cc:97-142), stop speculating down improbable branches, and pull workers off
 // nodes that became useless (ABANDON, masterloop.cc:70-82).  Each flush advances every active
 // worker by one batch: one evaluator.range() call per distinct item range.  Update styles as in
-// worker.hh:141-147 (FAST_SLOW / LOGARITHMIC: one probe batch, then the rest; INCREMENTAL: fixed batches).
+// worker.hh:141-147 (FAST_SLOW: one probe batch, then the rest; INCREMENTAL: fixed batches; LOGARITHMIC: like
+// FAST_SLOW, and the worker's probe batch doubles with every job it starts from item 0).
+//
+// FAILURE.  An evaluator that exposes `bool failed() const` (the GPU engine's does) is asked after every call; on
+// the first failure the batch's UPDATEs are dropped -- their sums are not results -- every inbox is emptied and
+// each virtual worker answers QUIT, so run_master returns at once instead of accepting every proposal on metric 0.
 //
 // Generic over the tree / record types on purpose: the oracle build instantiates this same
 // header with the REFERENCE's JobTree and records and a CPU evaluator to produce the golden
@@ -85,6 +90,7 @@ class FrontierCommunicator {
           eager_(eager_proposals), batch_items_(batch_items >= data_size ? 0 : batch_items),
           update_style_(update_style), inbox_(workers + 1), proposals_(workers + 1), updates_(workers + 1),
           work_(workers + 1) {
+        for (Work& w : work_) w.batch = batch_items_;
         for (int r = 1; r <= workers; ++r) {  // worker.hh:66,74
             push(r, FC_REGISTER);
             push(r, FC_WANTWORK);
@@ -93,9 +99,10 @@ class FrontierCommunicator {
 
     int size() const { return (int) inbox_.size(); }
     const FrontierStats& stats() const { return stats_; }
+    bool failed() const { return failed_; }
 
     std::optional<Status> iprobe(int rank, int) {
-        if (queued_ == 0) {
+        if (queued_ == 0 && !failed_) {
             if (batch_items_ == 0) {
                 if (!batch_.empty()) flush();
             } else
@@ -123,9 +130,10 @@ class FrontierCommunicator {
 
     Request isend(int rank, int, const JobInfoT& job_in) {
         if (job_in.id == 0) {  // the stop job (masterloop.cc:46-49); a worker answers QUIT (worker.hh:79-80)
-            push(rank, FC_QUIT);
+            if (!failed_) push(rank, FC_QUIT);
             return Request();
         }
+        if (failed_) return Request();  // the QUITs are already queued: hand-outs of the dying burst go nowhere
         JobInfoT job(job_in);
         ProposalInfoT proposal;
         const auto t0 = std::chrono::steady_clock::now();
@@ -204,9 +212,10 @@ class FrontierCommunicator {
                 continue;
             }
             std::size_t stop;
-            if (update_style_ == 1 || w.position == 0)  // worker.hh:141-147
-                stop = w.position + batch_items_;
-            else
+            if (update_style_ == 1 || w.position == 0) {  // worker.hh:141-147
+                stop = w.position + w.batch;
+                if (update_style_ == 2) w.batch *= 2;  // LOGARITHMIC: this WORKER's probe batch doubles per job
+            } else
                 stop = data_size_;
             if (stop > data_size_) stop = data_size_;
             const std::size_t count = stop - w.position;
@@ -227,6 +236,7 @@ class FrontierCommunicator {
             sum_sq_.assign(n, 0.0);
             const auto t0 = std::chrono::steady_clock::now();
             evaluator_.range(batch_, g.first, g.count, sum_, sum_sq_);
+            if (evaluator_failed(evaluator_, 0)) return fail();
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             stats_.eval_seconds += dt;
             ++stats_.engine_calls;
@@ -260,6 +270,26 @@ class FrontierCommunicator {
         batch_.clear();
     }
 
+    template <class E>
+    static auto evaluator_failed(const E& ev, int) -> decltype(ev.failed()) { return ev.failed(); }
+    template <class E>
+    static bool evaluator_failed(const E&, long) { return false; }
+
+    // the evaluator reported an error: nothing it returned is a result.  Drop everything in flight and let every
+    // virtual worker QUIT, which ends run_master (masterloop.cc:89-98) without another level being decided.
+    void fail() {
+        failed_ = true;
+        batch_.clear();
+        for (Work& w : work_) w.active = false;
+        queued_ = 0;
+        for (int r = 1; r < (int) inbox_.size(); ++r) {
+            inbox_[r].clear();
+            proposals_[r].clear();
+            updates_[r].clear();
+            push(r, FC_QUIT);
+        }
+    }
+
     void push(int rank, int tag) {
         inbox_[rank].push_back(tag);
         ++queued_;
@@ -275,6 +305,7 @@ class FrontierCommunicator {
         sum_sq_.assign(n, 0.0);
         const auto t0 = std::chrono::steady_clock::now();
         evaluator_(batch_, sum_, sum_sq_);
+        if (evaluator_failed(evaluator_, 0)) return fail();
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         stats_.eval_seconds += dt;
         ++stats_.engine_calls;
@@ -314,6 +345,7 @@ class FrontierCommunicator {
     std::vector<Work> work_;
     std::vector<double> sum_, sum_sq_;
     std::size_t queued_ = 0;
+    bool failed_ = false;
     FrontierStats stats_;
 };
 

@@ -1,3 +1,20 @@
+/* Derived from Fetching (elaine84/fetching): masterloop.cc (JobTree::run_master), statement for statement, with the locals renamed.
+ *
+ * Fetching
+ * Elaine Angelino, Eddie Kohler
+ * Copyright (c) 2012-2014 President and Fellows of Harvard College
+ *
+ * Permission is hereby granted, free of charge, to any person obtaining a
+ * copy of this software and associated documentation files (the "Software"),
+ * to deal in the Software without restriction, subject to the conditions
+ * listed in the Fetching LICENSE file. These conditions include: you must
+ * preserve this copyright notice, and you cannot mention the copyright
+ * holders in advertising related to the Software without their permission.
+ * The Software is provided WITHOUT ANY WARRANTY, EXPRESS OR IMPLIED. This
+ * notice is a summary of the Fetching LICENSE file; the license in that file
+ * is legally binding.  (The licence text is reproduced in LICENSE.fetching
+ * next to this file.)
+ */
 // host/master_loop.hpp -- the master's event loop over the Communicator concept.
 //
 // Same protocol as JobTree::run_master (masterloop.cc:21-134): poll the workers round-robin,

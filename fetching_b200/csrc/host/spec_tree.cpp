@@ -1,5 +1,24 @@
-// host/spec_tree.cpp -- see spec_tree.hpp.  Reference semantics cited per function
-// (master.cc of elaine84/fetching); the code is an independent implementation.
+/* Derived from Fetching (elaine84/fetching): master.cc (JobNode / JobTree), function for function, with the names changed.
+ *
+ * Fetching
+ * Elaine Angelino, Eddie Kohler
+ * Copyright (c) 2012-2014 President and Fellows of Harvard College
+ *
+ * Permission is hereby granted, free of charge, to any person obtaining a
+ * copy of this software and associated documentation files (the "Software"),
+ * to deal in the Software without restriction, subject to the conditions
+ * listed in the Fetching LICENSE file. These conditions include: you must
+ * preserve this copyright notice, and you cannot mention the copyright
+ * holders in advertising related to the Software without their permission.
+ * The Software is provided WITHOUT ANY WARRANTY, EXPRESS OR IMPLIED. This
+ * notice is a summary of the Fetching LICENSE file; the license in that file
+ * is legally binding.  (The licence text is reproduced in LICENSE.fetching
+ * next to this file.)
+ */
+// host/spec_tree.cpp -- see spec_tree.hpp.  A DERIVED WORK of the reference's master.cc (notice above): the
+// same functions in the same order under other names, kept in-tree so that pf_chain_run works where
+// /root/reference does not exist (the GPU box).  The reference's own JobTree drives the same engine through the
+// same FrontierCommunicator in oracle/ref_driver.cc (`pf_ref frontier --engine gpu`), which is the drop-in proof.
 #include "spec_tree.hpp"
 
 #include <cassert>

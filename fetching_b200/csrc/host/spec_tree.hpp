@@ -1,7 +1,24 @@
+/* Derived from Fetching (elaine84/fetching): master.hh (JobNode / JobTree declarations).
+ *
+ * Fetching
+ * Elaine Angelino, Eddie Kohler
+ * Copyright (c) 2012-2014 President and Fellows of Harvard College
+ *
+ * Permission is hereby granted, free of charge, to any person obtaining a
+ * copy of this software and associated documentation files (the "Software"),
+ * to deal in the Software without restriction, subject to the conditions
+ * listed in the Fetching LICENSE file. These conditions include: you must
+ * preserve this copyright notice, and you cannot mention the copyright
+ * holders in advertising related to the Software without their permission.
+ * The Software is provided WITHOUT ANY WARRANTY, EXPRESS OR IMPLIED. This
+ * notice is a summary of the Fetching LICENSE file; the license in that file
+ * is legally binding.  (The licence text is reproduced in LICENSE.fetching
+ * next to this file.)
+ */
 // host/spec_tree.hpp -- the speculative (prefetching) Metropolis-Hastings tree.
 //
-// Behavioural twin of JobTree / JobNode in the reference (master.hh, master.cc), written from
-// scratch: same node semantics, same id allocation, same random draws in the same order, same
+// JobTree / JobNode of the reference (master.hh, master.cc) under other names -- a derived work, see the
+// notice above: same node semantics, same id allocation, same random draws in the same order, same
 // accept test, same trimming -- so that, driven by the same message sequence, it hands out the
 // same JobInfos and prints the same chain.  (Parity is tested against traces produced by the
 // reference's own tree: tests/golden/frontier_trace_*.tsv.)

@@ -96,6 +96,27 @@ PeerXchg Engine::next_xchg() {
 
 static bool peer_active(const Engine& e) { return e.peer_fused && e.nranks > 1 && !e.node_split; }
 
+// The engine has one set of scratch buffers (records, ticket, panel, exchange sequence): a launch on a stream other
+// than the previous launch's is ordered behind it.  Costs nothing while the caller stays on one stream.
+static int order_streams(Engine& e, cudaStream_t s) {
+    if (e.last_stream != nullptr && e.last_stream != s) {
+        if (!e.order_event && cudaEventCreateWithFlags(&e.order_event, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return PF_ERR_CUDA;
+        }
+        if (cudaEventRecord(e.order_event, e.last_stream) != cudaSuccess ||
+            cudaStreamWaitEvent(s, e.order_event, 0) != cudaSuccess) {
+            cudaGetLastError();  // e.g. the caller destroyed the previous stream: fall back to a full barrier
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                set_error("cudaDeviceSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return PF_ERR_CUDA;
+            }
+        }
+    }
+    e.last_stream = s;
+    return PF_OK;
+}
+
 static int allreduce_out(Engine& e, double* d_out, uint32_t B, cudaStream_t s) {
     if (peer_active(e)) return PF_OK;  // already reduced inside the frontier kernel (peer_allreduce)
     if (!e.nccl_comm || e.nranks <= 1 || e.node_split) return PF_OK;
@@ -121,7 +142,8 @@ static bool is_matvec(const Engine& e) {
 
 static int launch_model(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
                         uint64_t n_items, cudaStream_t s) {
-    int r;
+    int r = order_streams(e, s);
+    if (r != PF_OK) return r;
     switch (e.desc.model) {
         case PF_MODEL_NORMAL:
         case PF_MODEL_MIXTURE: r = launch_pointwise(e, B, d_theta, d_out, first_item, n_items, s); break;
@@ -171,6 +193,7 @@ static void destroy(Engine* e) {
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_trace) cudaFreeHost(e->h_trace);
+    if (e->order_event) cudaEventDestroy(e->order_event);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -365,10 +388,23 @@ static int create(const pf_model_desc* d, Engine** out) {
 // Collect the n result doubles the kernel's last CTA delivers as self-validating words in mapped host memory
 // (PointwiseArgs::done_flag): polling beats copy + synchronise by ~15 us per call and needs no fence on the device
 // side; falls back to the stream's status so that a failed kernel cannot hang the caller.
+// Bounded: a kernel that neither delivers nor fails within PF_HOST_TIMEOUT_S seconds (default 120; far beyond any
+// frontier pass, and beyond the 20 s in-kernel peer timeout) is reported as PF_ERR_CUDA and the engine is marked
+// wedged -- every later call fails at once instead of hanging its caller behind a stuck stream.
+static double host_timeout_s() {
+    static double t = -1.0;
+    if (t < 0.0) {
+        const char* v = getenv("PF_HOST_TIMEOUT_S");
+        t = v && atof(v) > 0.0 ? atof(v) : 120.0;
+    }
+    return t;
+}
+
 static int wait_words(Engine& e, unsigned n, unsigned long long seq, double* vals) {
     volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(e.h_out);
     const unsigned long long tag = seq & 0xFFFFFFFFull;
     unsigned long long spins = 0;
+    timespec t_start = {0, 0};
     for (unsigned i = 0; i < n; ++i) {
         for (;;) {
             const unsigned long long lo = w[2 * i], hi = w[2 * i + 1];
@@ -388,6 +424,15 @@ static int wait_words(Engine& e, unsigned n, unsigned long long seq, double* val
                 }
                 if (q != cudaErrorNotReady) {
                     set_error("stream error while waiting for the frontier kernel: %s", cudaGetErrorString(q));
+                    return PF_ERR_CUDA;
+                }
+                timespec now;
+                clock_gettime(CLOCK_MONOTONIC, &now);
+                if (t_start.tv_sec == 0 && t_start.tv_nsec == 0) t_start = now;
+                if ((double) (now.tv_sec - t_start.tv_sec) + 1e-9 * (double) (now.tv_nsec - t_start.tv_nsec) > host_timeout_s()) {
+                    e.wedged = true;
+                    set_error("the frontier kernel delivered nothing within %.0f s (PF_HOST_TIMEOUT_S): engine marked unusable",
+                              host_timeout_s());
                     return PF_ERR_CUDA;
                 }
             }
@@ -436,7 +481,7 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
     }
     const uint32_t lo = (uint32_t) e.rank * per;
     const uint32_t nloc = lo >= B ? 0 : (B - lo < per ? B - lo : per);
-    if (node_split_fusable(e, B) && n_items > 0 && first_item * e.item_rows < e.n_rows) {
+    if (node_split_fusable(e, B)) {  // (the data set is replicated: an empty range is empty on every rank)
         // every rank has at least one node and the whole frontier fits one record: the frontier kernel of my slice
         // stores its sums into every peer's exchange buffer and gathers everybody's itself (PeerXchg gather mode):
         // one kernel, results + completion flag in mapped host memory
@@ -501,7 +546,20 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
 
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                      const uint64_t* order, double* sum, double* sum_sq) {
+    if (e.wedged) {
+        set_error("engine unusable: an earlier frontier kernel never completed");
+        return PF_ERR_CUDA;
+    }
     if (e.node_split && e.nranks > 1 && !order) return eval_host_node_split(e, B, thetas, first_item, n_items, sum, sum_sq);
+    if (e.nranks > 1 && e.desc.model == PF_MODEL_BOLTZMANN_SCALAR) {
+        set_error("the scalar Boltzmann model has no data to shard: not available on an engine group");
+        return PF_ERR_UNSUPPORTED;
+    }
+    const bool empty = n_items == 0 || first_item * e.item_rows >= e.n_rows;
+    if (empty && e.nranks <= 1) {  // nothing to score and nobody to exchange with
+        for (uint32_t b = 0; b < B; ++b) sum[b] = sum_sq[b] = 0.0;
+        return PF_OK;
+    }
     PF_CUDA(cudaSetDevice(e.device));
     for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
         const uint32_t nb = B - b0 < e.max_frontier ? B - b0 : e.max_frontier;
@@ -510,8 +568,9 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         const size_t tbytes = (size_t) nb * e.theta_len * 8;
         // Fast path: one frontier kernel whose last CTA writes the 2*nb results into mapped host memory and then
         // publishes a sequence number.  Row-sharded groups reduce inside the same kernel (peer_allreduce).  Not for NCCL-reduced results, ordered ranges, the scalar model or empty ranges.
-        const bool fast = !order && (e.nranks <= 1 || peer_active(e)) && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR && n_items > 0 &&
-                          first_item * e.item_rows < e.n_rows;
+        // Whether a rank is on this path must not depend on its LOCAL range: a rank of a peer group whose range is
+        // empty still launches (launch_exchange_only) so that its peers' kernels find its record.
+        const bool fast = !order && (e.nranks <= 1 || peer_active(e)) && e.desc.model != PF_MODEL_BOLTZMANN_SCALAR;
         // Small frontiers of the pointwise models ride in the kernel parameters (PointwiseArgs::theta_inline); anything
         // else goes through a DMA copy (letting ~300 CTAs read theta from mapped host memory was measured SLOWER,
         // 56 vs 37 us per call for the normal target -- hundreds of small PCIe reads in front of the compute).
@@ -623,6 +682,15 @@ int pf_engine_model(const pf_engine* e) { return e ? reinterpret_cast<const Engi
 uint32_t pf_engine_dim(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->dim : 0; }
 
 uint32_t pf_engine_components(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->K : 0; }
+
+int pf_engine_group(const pf_engine* pe, int* rank, int* nranks, int* node_split) {
+    if (!pe) return PF_ERR_INVALID;
+    const Engine& e = *reinterpret_cast<const Engine*>(pe);
+    if (rank) *rank = e.rank;
+    if (nranks) *nranks = e.nranks;
+    if (node_split) *node_split = e.node_split ? 1 : 0;
+    return PF_OK;
+}
 
 uint64_t pf_engine_launch_count(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->launches : 0; }
 
@@ -774,6 +842,19 @@ int pf_nccl_unique_id(void* id128) {
 int pf_engine_comm_init(pf_engine* pe, const void* id128, int rank, int nranks) {
     if (!pe || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PF_ERR_INVALID;
     Engine& e = *reinterpret_cast<Engine*>(pe);
+    if (e.nccl_comm) {
+        pf::set_error("pf_engine_comm_init: this engine already has a communicator (create a new engine to regroup)");
+        return PF_ERR_INVALID;
+    }
+    if (e.peer_attached && (rank != e.rank || nranks != e.nranks)) {
+        pf::set_error("pf_engine_comm_init: rank %d of %d contradicts the attached peer group (rank %d of %d)", rank, nranks,
+                      e.rank, e.nranks);
+        return PF_ERR_INVALID;
+    }
+    if (nranks > 1 && e.desc.model == PF_MODEL_BOLTZMANN_SCALAR) {
+        pf::set_error("the scalar Boltzmann model has no data to shard: not available on an engine group");
+        return PF_ERR_UNSUPPORTED;
+    }
     e.rank = rank;
     e.nranks = nranks;
     if (nranks == 1) return PF_OK;

@@ -141,6 +141,11 @@ struct Engine {
     unsigned long long* d_trace = nullptr;
     PeerXchg next_xchg();                  // arguments for the next launch (advances the call number)
     uint64_t launches = 0;
+    // One set of scratch buffers => launches are serialised across streams: `order_event` is recorded behind every
+    // launch and waited on by the next launch that goes to a different stream (pf_eval_frontier_device).
+    cudaEvent_t order_event = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool wedged = false;  // a frontier kernel never completed (wait_words timed out): every later call fails
 };
 
 // launchers (defined in the .cu files); return the number of kernels launched or <0 on error
@@ -152,6 +157,9 @@ int launch_normal_ordered(Engine& e, uint32_t B, const double* d_theta, double* 
                           const unsigned long long* d_order, uint64_t first_item, uint64_t n_items, cudaStream_t s);
 int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,
                             cudaStream_t s);
+// a rank of a peer-exchange group with NO rows in the requested range: takes part in the exchange with zeros
+int launch_exchange_only(Engine& e, uint32_t B, double* d_out, cudaStream_t s, unsigned out_off = 0,
+                         unsigned out_stride = 0);
 uint32_t pointwise_max_frontier(const Engine& e);
 int ensure_exp_table_for(Engine& e);  // uploads the mixture loop's exp table to e.device (once per device)
 bool pointwise_supported(const Engine& e);

@@ -662,12 +662,9 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     a.inv_temperature = 1.0 / e.temperature;
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
-    a.xchg = e.next_xchg();
     a.trace = e.d_trace;
-    if (a.row_end <= a.row_begin) {
-        cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
-        return 0;
-    }
+    if (a.row_end <= a.row_begin) return launch_exchange_only(e, B, d_out, s);  // no rows here: zeros (+ the exchange)
+    a.xchg = e.next_xchg();
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
     static bool prep_configured[64] = {};

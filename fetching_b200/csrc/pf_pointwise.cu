@@ -1046,11 +1046,16 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     a.K = e.K;
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
-    a.xchg = e.next_xchg();
-    if (a.row_end <= a.row_begin) {
-        cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * B, s);
-        return 0;
+    if (a.row_end <= a.row_begin) {  // no rows here: zeros (+ the same exchanges the other ranks' launches make)
+        if (e.desc.model == PF_MODEL_MIXTURE && !e.f32 && B > 32 && e.gather_per == 0) {
+            const int r1 = launch_exchange_only(e, 32, d_out, s, 0, B);
+            if (r1 < 0) return r1;
+            const int r2 = launch_exchange_only(e, B - 32, d_out, s, 32, B);
+            return r2 < 0 ? r2 : r1 + r2;
+        }
+        return launch_exchange_only(e, B, d_out, s);
     }
+    a.xchg = e.next_xchg();
     if (e.desc.model == PF_MODEL_NORMAL) {
         // The general-covariance variant reproduces the identity result exactly (W = I), so it is
         // always correct; the identity fast path is chosen by the caller when every node's
@@ -1134,6 +1139,46 @@ int launch_normal_ordered(Engine& e, uint32_t B, const double* d_theta, double* 
 #undef PF_ORD_CASE
     set_error("normal target: dimension %u not built", e.dim);
     return -1;
+}
+
+// An empty local range on a rank of a peer-exchange group: one CTA that contributes zeros to the exchange (so the
+// peers' kernels, which wait for this rank's record, and the call numbering stay in step) and delivers the totals
+// exactly like a frontier kernel's finalizing CTA.  Without peers the result is simply zero.
+__global__ void __launch_bounds__(256) exchange_only_kernel(const PeerXchg x, unsigned B, double* out,
+                                                            unsigned long long* done_flag,
+                                                            unsigned long long done_seq, unsigned out_off,
+                                                            unsigned out_stride) {
+    __shared__ double scratch[2 * kMaxNodesPerPass];
+    const unsigned tid = threadIdx.x;
+    double S = 0.0, Q = 0.0;
+    unsigned Bout = B;
+    if (x.nranks > 1) {
+        const double2 t = peer_allreduce(x, tid, B, 256, 1, scratch, S, Q);
+        S = t.x;
+        Q = t.y;
+        if (x.gather_per) Bout = x.gather_total;
+    }
+    if (tid < Bout) {
+        const unsigned iS = out_off + tid, iQ = (out_stride ? out_stride : Bout) + out_off + tid;
+        if (done_flag) {
+            store_result_words(out, iS, S, done_seq);
+            store_result_words(out, iQ, Q, done_seq);
+        } else {
+            out[iS] = S;
+            out[iQ] = Q;
+        }
+    }
+}
+
+int launch_exchange_only(Engine& e, uint32_t B, double* d_out, cudaStream_t s, unsigned out_off, unsigned out_stride) {
+    const PeerXchg x = e.next_xchg();
+    exchange_only_kernel<<<1, 256, 0, s>>>(x, B, d_out, e.done_flag, e.done_seq, out_off, out_stride);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("exchange_only_kernel launch: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 1;
 }
 
 int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t n_items,

@@ -119,6 +119,9 @@ PF_API uint32_t pf_engine_max_frontier(const pf_engine* e); /* nodes scored per 
 PF_API int pf_engine_model(const pf_engine* e);           /* enum pf_model */
 PF_API uint32_t pf_engine_dim(const pf_engine* e);
 PF_API uint32_t pf_engine_components(const pf_engine* e);
+/* Multi-GPU group of this engine: *rank / *nranks as set by pf_engine_peer_attach / pf_engine_comm_init (0 / 1 for
+ * a single engine), *node_split = PF_OPT_NODE_SPLIT.  Any pointer may be NULL. */
+PF_API int pf_engine_group(const pf_engine* e, int* rank, int* nranks, int* node_split);
 
 /* Score B frontier nodes over ALL items.  thetas: HOST [B][theta_len]; sum, sum_sq: HOST [B]
  * (overwritten).  The thetas reach the device in the kernel parameters (small frontiers of the pointwise
@@ -144,7 +147,11 @@ PF_API int pf_eval_frontier_range(pf_engine* e, uint32_t B, const double* thetas
 
 /* Device-resident variant: d_thetas [B][theta_len] and d_out [2][B] (sums, then sums of
  * squares) are DEVICE pointers; work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the
- * engine's own stream) and the call returns without synchronising.  B <= pf_engine_max_frontier. */
+ * engine's own stream) and the call returns without synchronising.  B <= pf_engine_max_frontier.
+ * An engine has ONE set of scratch buffers (per-CTA records, ticket, coefficient panel, exchange sequence):
+ * it is not reentrant.  Calls on different streams are ordered by the engine itself (an event recorded behind
+ * each launch, waited on by the next launch that uses another stream), so they never overlap; for concurrency
+ * create one engine per stream. */
 PF_API int pf_eval_frontier_device(pf_engine* e, uint32_t B, const double* d_thetas, double* d_out,
                             void* cuda_stream);
 
@@ -168,8 +175,12 @@ PF_API int pf_engine_comm_init(pf_engine* e, const void* id128, int rank, int nr
  *                                rank / nranks like pf_engine_comm_init and selects the fused exchange
  *   pf_engine_peer_attach_local  all engines of the group live in THIS process (any devices): no IPC
  *   pf_engine_peer_status        PF_ERR_NCCL after a call in which some rank never arrived (20 s timeout)
- * Every rank must make the same sequence of evaluation calls (as with any collective). nranks <= 16.  An engine
- * is attached once: regrouping means new engines. */
+ * Every rank must make the same sequence of evaluation calls (as with any collective), with the same B and, for
+ * pf_eval_frontier_range, any LOCAL item range it likes -- a rank whose range is empty (n_items == 0) still takes
+ * part in the exchange and contributes zeros.  nranks <= 16.  An engine is attached once: regrouping means new
+ * engines.  The scalar Boltzmann model has no data to shard and refuses to be grouped (PF_ERR_UNSUPPORTED).
+ * pf_chain_run on a row-sharded group runs the same deterministic chain on every rank: every rank must hold the
+ * SAME number of items (the chain sees nranks x that many) and pass the same configuration. */
 PF_API int pf_engine_peer_export(pf_engine* e, void* handle64);
 PF_API int pf_engine_peer_attach(pf_engine* e, const void* handles, int rank, int nranks);
 PF_API int pf_engine_peer_attach_local(pf_engine* const* engines, int nranks);

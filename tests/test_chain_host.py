@@ -183,3 +183,101 @@ def test_shared_noise_and_stream_do_not_change_proposals(orc):
                                            initial_theta=init) for f in (1, 16)]
     assert np.array_equal(runs[0].theta, runs[1].theta) and np.array_equal(runs[0].accept, runs[1].accept)
     assert np.all(runs[0].theta[:, 0] > 0)
+
+
+def test_failing_evaluator_stops_the_chain(orc):
+    """An engine failure must end the chain at once: no level may be decided on the zeroed sums of a
+    failed call, no further evaluator call is made, and the error comes back as the status."""
+    from fetching_b200 import _lib, chain
+    data = orc.normal_dataset(10000)
+    calls = []
+
+    def ev(th):
+        calls.append(len(th))
+        if len(calls) == 4:
+            return _lib.PF_ERR_CUDA
+        return orc.normal_frontier(data, th)
+
+    good = chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, lambda th: orc.normal_frontier(data, th),
+                                          chain_length=200, frontier=8)
+    bad = chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, ev, chain_length=200, frontier=8,
+                                         check_status=False)
+    assert bad.status == _lib.PF_ERR_CUDA
+    assert len(calls) == 4                      # nothing was evaluated after the failure
+    n = len(bad.depth)
+    assert 0 < n < len(good.depth)              # the chain stopped early ...
+    assert np.array_equal(bad.theta, good.theta[:n]) and np.array_equal(bad.accept, good.accept[:n])  # ... and every
+    assert np.array_equal(bad.metric_sum, good.metric_sum[:n])  # row it did deliver is a row of the healthy chain
+    with pytest.raises(_lib.PfetchError):
+        chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, lambda th: _lib.PF_ERR_CUDA, chain_length=50,
+                                       frontier=4)
+
+
+def test_failing_range_evaluator_stops_the_chain(orc):
+    from fetching_b200 import _lib, chain
+    data = orc.normal_dataset(10000)
+    calls = []
+
+    def ev_range(th, first, count, order):
+        calls.append((first, count))
+        if len(calls) == 7:
+            return _lib.PF_ERR_NCCL
+        out = np.array([orc.normal_eval(data, t, int(o[0]), int(o[1]), first, count) for t, o in zip(th, order)])
+        return out[:, 0], out[:, 1]
+
+    bad = chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, lambda th: orc.normal_frontier(data, th),
+                                         chain_length=100, frontier=8, batch_items=1000, range_evaluator=ev_range,
+                                         check_status=False)
+    assert bad.status == _lib.PF_ERR_NCCL and len(calls) == 7
+
+
+@pytest.mark.parametrize("style", [0, 2])
+def test_probe_batch_styles_leave_the_chain_alone(orc, style):
+    """-y 0 (FAST_SLOW) and -y 2 (LOGARITHMIC, worker.hh:141-147: the worker's probe batch doubles with every job it
+    starts from item 0): same chain as whole-node scoring; with style 2 the probe batches of a worker grow."""
+    from fetching_b200 import _lib, chain
+    data = orc.normal_dataset(10000)
+    ranges = []
+
+    def ev_range(th, first, count, order):
+        ranges.append((first, count, len(th)))
+        out = np.array([orc.normal_eval(data, t, int(o[0]), int(o[1]), first, count) for t, o in zip(th, order)])
+        return out[:, 0], out[:, 1]
+
+    ev = lambda th: orc.normal_frontier(data, th)
+    whole = chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, ev, chain_length=50, frontier=4)
+    part = chain.run_chain_with_evaluator(_lib.MODEL_NORMAL, 2, 0, 10000, ev, chain_length=50, frontier=4,
+                                          batch_items=100, update_style=style, range_evaluator=ev_range)
+    n = min(len(whole.depth), len(part.depth))
+    assert n >= 51
+    assert np.array_equal(whole.theta[:n], part.theta[:n]) and np.array_equal(whole.accept[:n], part.accept[:n])
+    assert np.max(np.abs(whole.metric_sum[:n] - part.metric_sum[:n]) / np.abs(whole.metric_sum[:n])) < 1e-10
+    probes = sorted({c for f, c, _ in ranges if f == 0})
+    if style == 0:
+        assert probes == [100]
+    else:
+        assert probes[0] == 100 and len(probes) > 2 and all(p % 100 == 0 and (p // 100) & (p // 100 - 1) == 0 or p == 10000
+                                                             for p in probes)
+
+
+def test_cli_resolves_samplers_through_the_registry():
+    """tree.cc:121-131: the sampler is looked up by name, an unknown name lists the registered ones, and the plugin
+    parses its own key=value arguments (set_arguments < 0 aborts).  None of this needs a GPU."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fetching_b200", "lib", "pfetch")
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, timeout=60)
+    p = run("nosuch")
+    assert p.returncode == 1 and p.stderr.startswith('No such sampler "nosuch"\n')
+    assert p.stderr.split("\n")[1:7] == ["normal", "boltzmann", "pymixture", "pyblasso", "py", "python"]
+    p = run("py")
+    assert p.returncode == 1 and "too few arguments, expected 'fetching py MODULE" in p.stderr
+    p = run("py", "numpy")
+    assert p.returncode == 1 and "No module named numpy" in p.stderr
+    p = run("pymixture", "train_size")
+    assert p.returncode == 1 and "expected key=value" in p.stderr
+    p = run("-S", "pymixture", "train_size=12x")
+    assert p.returncode == 1 and "not an integer" in p.stderr
+    p = run("-f")
+    assert p.returncode == 1
+    p = run("-h")
+    assert p.returncode == 0 and all(f in p.stdout for f in ("-b BATCH", "-y STYLE", "-u USEC", "-S NAME"))
