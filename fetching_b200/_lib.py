@@ -54,6 +54,7 @@ class ChainStats(C.Structure):
         ("max_frontier", C.c_uint64), ("allocated_nodes", C.c_uint64), ("recycled_nodes", C.c_uint64),
         ("seconds", C.c_double), ("eval_seconds", C.c_double), ("items_scored", C.c_uint64),
         ("abandoned", C.c_uint64), ("accepted", C.c_uint64),
+        ("min_margin", C.c_double), ("min_margin_rel", C.c_double),
     ]
 
 

@@ -180,6 +180,8 @@ static int run_chain(const ChainTarget& tg, Executor& ex, const pf_chain_config&
         stats->items_scored = comm.stats().items_scored;
         stats->abandoned = comm.stats().abandoned + comm.stats().skipped;
         stats->accepted = hook.accepted();
+        stats->min_margin = tree.min_margin();
+        stats->min_margin_rel = tree.min_margin_rel();
     }
     return eval.status;
 }

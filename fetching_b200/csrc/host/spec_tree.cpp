@@ -277,6 +277,15 @@ void SpecTree::trim(const run_behavior& rb, double master_wait_time, double mast
     assert(child->complete() && child->depth_ == child->true_depth_ && child->has_final_branch_probability());
     const bool accept = child->branch_probability_ > 0.5;
     assert(child->child_[accept] && !child->child_[!accept]);
+    if (const SpecNode* cp = child->comparison_parent_) {  // how close this level's test (master.cc:89) was to flipping
+        const double lhs = (child->log_prior_ - cp->log_prior_) + child->metric_sum() - cp->metric_sum();
+        const double margin = std::fabs(lhs - child->log_u_);
+        const double mag = std::max(std::fabs(child->metric_sum()), std::fabs(cp->metric_sum()));
+        if (std::isfinite(margin)) {
+            min_margin_ = std::min(min_margin_, margin);
+            if (mag > 0.0) min_margin_rel_ = std::min(min_margin_rel_, margin / mag);
+        }
+    }
 
     if (!rb.quiet) {  // the -p table (master.cc:324-345)
         if (child->depth_ == 1)

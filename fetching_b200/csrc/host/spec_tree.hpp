@@ -141,6 +141,11 @@ class SpecTree {
     std::size_t recycled_nodes() const { return recycled_nodes_; }
     double local_accept_rate() const { return accept_count_ / 100.; }
     double reassign_ratio() const { return reassign_ratio_; }
+    // smallest |delta_log_prior + metric_sum - parent.metric_sum - log_u| over the levels decided so far, and the
+    // smallest such margin relative to max(|metric_sum|, |parent.metric_sum|): how far the chain's accept / reject
+    // decisions were from flipping under an error in the sums (infinity before the first decision)
+    double min_margin() const { return min_margin_; }
+    double min_margin_rel() const { return min_margin_rel_; }
 
     std::pair<std::size_t, double> high_utility_pending(std::size_t stopper = 0);
     JobInfo execute(std::size_t id, int executor);
@@ -188,6 +193,8 @@ class SpecTree {
     double wasted_proposal_time_ = 0.0, wasted_step_time_ = 0.0, useful_proposal_time_ = 0.0,
            useful_step_time_ = 0.0;
     std::vector<double> wait_time_;
+    double min_margin_ = std::numeric_limits<double>::infinity(),
+           min_margin_rel_ = std::numeric_limits<double>::infinity();
 };
 
 std::ostream& operator<<(std::ostream& s, const SpecTree& tree);

@@ -227,6 +227,10 @@ typedef struct pf_chain_stats {
     uint64_t items_scored;  /* sum over engine calls of nodes x items: the work paid for */
     uint64_t abandoned;     /* nodes dropped before completion (ABANDON, or found dead) */
     uint64_t accepted;      /* accepted proposals among levels 1.. (the chain's acceptance count) */
+    double min_margin;      /* min over decided levels of |delta_log_prior + sum - parent_sum - log u| (master.cc:89):
+                               an error in the sums smaller than this flips no accept / reject decision */
+    double min_margin_rel;  /* min of that margin / max(|sum|, |parent_sum|): compare with the 1e-10 (FP64) or
+                               1e-5 (FP32) relative tolerance of the sums; +inf before the first decision */
 } pf_chain_stats;
 
 typedef void (*pf_chain_row_fn)(void* user, uint64_t depth, int accept, double metric_sum, const double* theta,

@@ -622,6 +622,24 @@ void orc_boltzmann_dense_frontier_mt(const double* W, size_t D, const double* X,
     }
 }
 
+/* bench.py only: fix the number of OpenMP threads explicitly (torchrun exports OMP_NUM_THREADS=1, which would
+ * otherwise turn the CPU baseline of a multi-GPU launch into a one-thread number); returns what is in force */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    extern void omp_set_dynamic(int);
+    extern int omp_get_max_threads(void);
+    if (n > 0) {
+        omp_set_dynamic(0);
+        omp_set_num_threads(n);
+    }
+    return omp_get_max_threads();
+#else
+    (void) n;
+    return 1;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         L.orc_boltzmann_dense_logp.restype = C.c_double
         L.orc_boltzmann_dense_frontier_mt.argtypes = [_dp, sz, _dp, sz, C.c_double, _dp, _dp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = C.c_int
         _lib = L
     return _lib
 
@@ -242,6 +244,11 @@ def blasso_log_prior(theta, tau=5.0):
 # ----------------------------------------------------------------------------- frontier (all host threads)
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def set_threads(n: int) -> int:
+    """Use exactly `n` OpenMP threads from now on, whatever OMP_NUM_THREADS says; returns the count in force."""
+    return int(lib().orc_set_threads(int(n)))
 
 
 def mixture_frontier(data, thetas, item_rows):

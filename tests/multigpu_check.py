@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N scripts/multigpu_check.py
+"""torchrun --nproc-per-node N tests/multigpu_check.py   (run by tests/test_gpu_multigpu.py when the box has >= 2 GPUs)
 
 Row-sharded engines against a single engine holding the whole data set on the rank's GPU, for the
 mixture and the lasso, with both reductions: the in-kernel peer exchange over NVLink (CUDA IPC handles,

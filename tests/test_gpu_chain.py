@@ -18,6 +18,17 @@ def fb():
     return fetching_b200
 
 
+def check_margins(res, tol=1e-10):
+    """report the accept / reject margins rather than assume.  The chain's decisions equal the
+    reference's as long as the error of the two sums in the test (master.cc:89) stays below the margin
+    |delta_log_prior + sum - parent_sum - log u|; the contract allows `tol` relative per sum, so the smallest margin
+    over the chain, relative to |sum|, has to clear 2 tol.  (The engine's actual error is ~1e-14: the kernels are
+    run-to-run bit-stable and differ from the oracle in the last digits only.)"""
+    m, r = res.stats["min_margin"], res.stats["min_margin_rel"]
+    print("min accept/reject margin %.3e (%.3e of |sum|) over %d levels" % (m, r, res.stats["levels"]))
+    assert r > 2 * tol, "a decision of this chain sits within the parity tolerance: margin %.3e of |sum|" % r
+
+
 def engine_for(fb, orc, model):
     if model == "normal":
         return fb.FrontierEngine.normal(orc.normal_dataset(10000))
@@ -46,6 +57,7 @@ def test_gpu_normal_chain_300_levels_vs_mastertester_golden(fb, orc):
     with engine_for(fb, orc, "normal") as e:
         res = chain.run_chain(e, chain_length=300, frontier=16)
     assert len(res.depth) == 301
+    check_margins(res)
     for i, g in enumerate(gold):
         assert (res.depth[i], res.accept[i], res.theta[i].tobytes()) == (g[0], g[1], g[3]), i
         assert abs(res.metric_sum[i] - g[2]) <= 1e-10 * abs(g[2])
@@ -61,6 +73,8 @@ def test_gpu_normal_chain_c1_full_size(fb, orc):
         a = chain.run_chain(e, chain_length=100, frontier=8)
         b = chain.run_chain(e, chain_length=100, frontier=64)
     assert np.array_equal(a.theta, b.theta) and np.array_equal(a.accept, b.accept)
+    check_margins(a)
+    assert a.stats["min_margin"] == pytest.approx(b.stats["min_margin"], rel=1e-6)
     # a node's sum is bit-stable for a given launch geometry; the lane mapping (hence the summation
     # order) follows the frontier size, so across B it agrees to rounding only
     assert np.max(np.abs(a.metric_sum - b.metric_sum) / np.abs(a.metric_sum)) < 1e-12
@@ -75,6 +89,7 @@ def test_gpu_normal_chain_d100000_golden(fb, orc):
     gold = orc.parse_chain(open(os.path.join(GOLD, "chain_normal_d100000.tsv")).read())
     with fb.FrontierEngine.normal(orc.normal_dataset(100000)) as e:
         res = chain.run_chain(e, chain_length=60, frontier=16)
+    check_margins(res)
     for i, g in enumerate(gold):
         assert (res.depth[i], res.accept[i], res.theta[i].tobytes()) == (g[0], g[1], g[3]), i
         assert abs(res.metric_sum[i] - g[2]) <= 1e-10 * abs(g[2])
@@ -88,6 +103,8 @@ def test_gpu_mixture_and_lasso_chains(fb, orc):
     with fb.FrontierEngine.mixture(data, 8, 1000) as e:
         got = chain.run_chain(e, chain_length=30, frontier=8, dimension=16)
     assert np.array_equal(got.theta, want.theta) and np.array_equal(got.accept, want.accept)
+    check_margins(got)
+    assert got.stats["min_margin"] == pytest.approx(want.stats["min_margin"], rel=1e-6)
     assert np.max(np.abs(got.metric_sum - want.metric_sum) / np.abs(want.metric_sum)) < 1e-10
 
     X, y, beta = models.blasso_dataset(6000, 20, seed=1)
@@ -98,6 +115,7 @@ def test_gpu_mixture_and_lasso_chains(fb, orc):
     with fb.FrontierEngine.blasso(X, y, item_rows=1000) as e:
         got = chain.run_chain(e, chain_length=30, frontier=8, dimension=21, initial_theta=init)
     assert np.array_equal(got.theta, want.theta) and np.array_equal(got.accept, want.accept)
+    check_margins(got)
     assert np.max(np.abs(got.metric_sum - want.metric_sum) / np.abs(want.metric_sum)) < 1e-10
 
 
@@ -142,5 +160,7 @@ def test_gpu_predictive_mode_on_mixture(fb, orc):
         whole = chain.run_chain(e, chain_length=60, frontier=16, dimension=16)
         part = chain.run_chain(e, chain_length=60, frontier=16, dimension=16, batch_items=20, update_style=0)
     assert np.array_equal(whole.theta[:61], part.theta[:61]) and np.array_equal(whole.accept[:61], part.accept[:61])
+    check_margins(whole)
+    check_margins(part)
     assert np.max(np.abs(whole.metric_sum[:61] - part.metric_sum[:61]) / np.abs(whole.metric_sum[:61])) < 1e-11
     assert part.stats["items_scored"] < 0.7 * whole.stats["items_scored"]

@@ -1,6 +1,8 @@
 """Parity at BASELINE.json's full sizes.  Where the oracle finishes in seconds it is the checker;
 for the 10^8-row mixture the checks are size-independent properties (additivity over item ranges,
 agreement with the oracle on random item windows, shard additivity) plus the oracle on a window."""
+import os
+
 import numpy as np
 import pytest
 
@@ -58,6 +60,11 @@ def test_c5_mixture_1e8_properties(fb, orc):
             w = orc.mixture_frontier(data[first * 1000:(first + 1000) * 1000], th, 1000)
             g = e.eval_frontier_range(th, first, 1000)
             assert rel(g[0], w[0]) < TOL64 and rel(g[1], w[1]) < TOL64
+        # ... and the oracle over ALL 10^8 rows (4 nodes x 10^8 rows: a few seconds on the host's threads)
+        orc.set_threads(len(os.sched_getaffinity(0)))
+        w = orc.mixture_frontier(data, th, 1000)
+        print("C5 full data, GPU vs oracle: rel err sum %.2e sum_sq %.2e" % (rel(s, w[0]), rel(q, w[1])))
+        assert rel(s, w[0]) < TOL64 and rel(q, w[1]) < TOL64
         # deterministic
         s2, q2 = e.eval_frontier(th)
         assert np.array_equal(s, s2) and np.array_equal(q, q2)
