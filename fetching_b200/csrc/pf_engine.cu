@@ -228,6 +228,7 @@ static int create(const pf_model_desc* d, Engine** out) {
     e->K = d->components;
     e->n_rows = d->n_rows;
     e->temperature = d->param != 0.0 ? d->param : 1.0;
+    for (double& v : e->xmax) v = HUGE_VAL;
 
     auto fail = [&](int code) {
         destroy(e);
@@ -320,6 +321,20 @@ static int create(const pf_model_desc* d, Engine** out) {
         PF_CUDA_F(cudaMemsetAsync(e->d_data, 0, bytes, e->stream));
         if (!e->f32) {
             PF_CUDA_F(cudaMemcpyAsync(e->d_data, d->data, elems * 8, cudaMemcpyHostToDevice, e->stream));
+            // while the copy runs: the data set's bounding box (max |x_j| per column; a NaN makes it +inf), which the
+            // mixture kernel tests theta against before it uses the factored form of the exponent (pf_math.cuh)
+            if (d->model == PF_MODEL_MIXTURE && e->dim <= 8) {
+                double mx[8] = {};
+                bool nan = false;
+                const uint32_t D = e->dim;
+                for (size_t r = 0; r < e->n_rows; ++r)
+                    for (uint32_t j = 0; j < D; ++j) {
+                        const double v = fabs(d->data[r * D + j]);
+                        nan |= v != v;
+                        mx[j] = v > mx[j] ? v : mx[j];
+                    }
+                for (uint32_t j = 0; j < D; ++j) e->xmax[j] = nan ? HUGE_VAL : mx[j];
+            }
             PF_CUDA_F(cudaStreamSynchronize(e->stream));
         } else {
             const size_t chunk = size_t(1) << 24;
@@ -602,6 +617,7 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
                         "last cta: enter %lld folded %lld end %lld (ns)\n", (long long) (t[1] - t[0]), (long long) (t[2] - t[0]),
                         (long long) (t[3] - t[0]), (long long) (t[4] - t[0]), (long long) (t[5] ? t[5] - t[0] : 0),
                         (long long) (t[16] - t[0]), (long long) (t[17] - t[0]), (long long) (t[18] - t[0]));
+                if (t[6]) fprintf(stderr, "[pf trace] mixture exponent form: %s\n", t[6] == 1 ? "factored" : "clamped distance");
                 std::vector<long long> in, out;
                 for (int c = 0; c < kMaxGrid; ++c)
                     if (t[32 + 2 * c]) {

@@ -56,6 +56,8 @@ struct PointwiseArgs {
                                           // (out_stride 0: the launch's own node count) -- a frontier scored in two launches
     unsigned long long* trace;            // diagnostics (PF_TRACE=1): %globaltimer marks of CTA 0 [0..15] and of the
                                           // finalizing CTA [16..31]; nullptr in normal operation
+    double xmax[8];                       // max |x_j| over the engine's rows per column (+inf: unknown / non-finite data):
+                                          // the bounding box the mixture kernel tests theta against (factored form)
     unsigned int theta_inline_n;          // doubles valid in theta_inline; 0: read `theta`
     double theta_inline[kInlineThetaDoubles];
 };
@@ -97,6 +99,7 @@ struct Engine {
     uint32_t dim = 0, K = 0, theta_len = 0, max_frontier = 64;
     uint32_t cols_pad = 0;
     double temperature = 1.0;
+    double xmax[8];              // pointwise models: max |x_j| per column of the resident rows (see PointwiseArgs)
     bool normal_general = true;  // per call: some node has a non-identity covariance (or unknown)
     bool assume_identity = false;  // PF_OPT_ASSUME_IDENTITY_COV
     bool mv_tensor = true;         // PF_OPT_MATVEC_TENSOR: DMMA variant of the matvec kernel (FP64 only)

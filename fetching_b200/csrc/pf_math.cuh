@@ -356,6 +356,7 @@ __device__ const double kLogTab[512] = {
 __constant__ double kAtanhC[10] = {1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0,  1.0 / 9.0,  1.0 / 11.0,
                                    1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0};
 constexpr double kNegHalfLog2e = -0.72134752044448170368;  // -log2(e)/2
+constexpr double kLog2e = 1.44269504088896340736;
 constexpr double kRintMagic = 26388279066624.0;            // 1.5 * 2^44: rint(256 z) lands in the low word
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
 
@@ -526,6 +527,125 @@ __device__ __forceinline__ double log_pos_fast_k(double x, unsigned ltab_s) {
     const double l1p = fma(r * r, p, r);
     const double nd = (double) n;
     return fma(nd, kLn2Head, fma(nd, kLn2Tail, t.y + l1p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mixture inner loop, third generation (the default).  What bounds the loop is measured, not assumed (ncu, round 2):
+// with the 2048-entry table the SHARED-MEMORY pipe carried 0.91 wavefronts per cycle per SM -- 59 % of them bank-conflict
+// replays of the eight random 8-byte table reads per (row, node): a half-warp's 16 lanes hit 16 bank pairs at random, so a
+// read takes ~6.5 wavefronts instead of 2 -- and removing FP64 instructions alone changed nothing (6.00 -> 5.95 ms).
+//
+// (a) CONFLICT-FREE table: 256 entries, each stored 16 times side by side (g_exp2_rep[j][c], 32 KB of shared memory), and
+//     lane l reads copy c = l mod 16, i.e. always bank pair l mod 16: every lookup is exactly 2 wavefronts.  With 256
+//     entries |g| <= 2^-9, where the degree-3 MINIMAX polynomial of 2^g (Chebyshev economisation of the Taylor series)
+//     is exact to 1.8e-14 relative.  Monic: 2^g = B3 (g^3 + Q2 g^2 + Q1 g + Q0), B3 folded into the table -- one constant
+//     per instruction (an FMA with two constants costs two re-materialising moves); entries carry (j << 12) subtracted
+//     from their high word so the exponent surgery is one IMAD (hi' + Z * 4096, Z = rint(256 z) = 256 k + j).
+// (b) "Factored" exponent (mix_exp_accumulate_z): |theta_k - x|^2 = |theta_k|^2 - 2 theta_k.x + |x|^2, and the |x|^2 part is
+//     the same for every component, so   log sum_k exp(-|theta_k - x|^2 / 2) = -|x|^2/2 + ln sum_k 2^(z_k),
+//         z_k = A_k + B_k . x,   A_k = -log2(e)/2 |theta_k|^2,   B_k = log2(e) theta_k   (per node, staged once per call):
+//     d FMAs per component instead of d subtractions + d multiply-adds + the scaling.  K = 8, d = 2: 9 FP64 instructions
+//     per component (2 z, 3 range reduction, 3 polynomial, 1 accumulate) against 11 before.  Rounding: z carries an absolute
+//     error of a few 2^-53 max(|A_k|, |B_k.x|); the kernel takes this path only when  |A_k| + sum_j |B_kj| max|x_j| <= 512
+//     for every component of every node (theta against the data set's bounding box, checked while theta is staged), which
+//     bounds the error of a term by 2e-13 relative in the worst corner and ~1e-15 for data like the benchmark's, keeps
+//     every 2^z a normal number, so no clamp, no slow path and no per-row range test are needed; anything else (far
+//     thetas, NaN / inf anywhere) runs the clamped distance form below (mix_exp_accumulate_e).
+// (c) log (log_pos_acc): degree-4 series on |r| <= 2^-9 (truncation r^5/5 <= 5.7e-15 absolute), and the exponent n is
+//     accumulated as an INTEGER over the lane's rows of a tile; n ln 2 is added once per tile -- 5 FP64 + the two
+//     accumulating adds per row instead of 10 + 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExpRepBits = 8, kExpRepSize = 1 << kExpRepBits, kExpRepCopies = 16;
+constexpr double kExp3Q2 = 4.3280852879260374, kExp3Q1 = 12.488212455522227, kExp3Q0 = 18.016682179149544;
+constexpr long double kExp3B3 = 0.05550411502275755523220807L;  // leading coefficient (in the table)
+constexpr double kRintMagicRep = 26388279066624.0;              // 1.5 * 2^44: rint(256 z) lands in the low word
+constexpr double kFactoredLimit = 512.0;  // bound on |z| under which the factored form is used
+// filled once per device by the host (ensure_exp_table): [256][16] copies of (long-double B3 2^(j/256), high word - (j << 12))
+__device__ __align__(128) double g_exp2_rep[kExpRepSize * kExpRepCopies];
+
+// one component: t = z + magic already formed; lp += 2^k T[j] (g^3 + Q2 g^2 + Q1 g + Q0).  `tab_l` is the shared-memory
+// address of THIS LANE's copy of entry 0 (table base + 8 (lane mod 16)); entries are 128 bytes apart.
+#define PF_MIX_EXP_CORE(tc, tjsc)                                                                 \
+    {                                                                                             \
+        const int Z = __double2loint(tc);                                                         \
+        unsigned idx, addr;                                                                       \
+        double tj;                                                                                \
+        asm("and.b32 %0, %1, %2;" : "=r"(idx) : "r"(Z), "n"(kExpRepSize - 1));                    \
+        asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(idx), "r"(tab_l));                   \
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));                                    \
+        tjsc = __hiloint2double(__double2hiint(tj) + Z * 4096, __double2loint(tj));               \
+    }
+#define PF_MIX_EXP_POLY(G)                                                 \
+    double P[G];                                                           \
+    _Pragma("unroll") for (int c = 0; c < G; ++c) P[c] = g[c] + kExp3Q2;   \
+    _Pragma("unroll") for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExp3Q1); \
+    _Pragma("unroll") for (int c = 0; c < G; ++c) P[c] = fma(P[c], g[c], kExp3Q0);
+
+// z given (|z| <= kFactoredLimit guaranteed by the caller): 7 FP64 + 4 other instructions per component
+template <int G, bool TWO_ACC>
+__device__ __forceinline__ void mix_exp_accumulate_z(const double (&z)[G], double& lp0, double& lp1, unsigned tab_l) {
+    double g[G], tjs[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        const double t = z[c] + kRintMagicRep;
+        g[c] = z[c] - (t - kRintMagicRep);
+        PF_MIX_EXP_CORE(t, tjs[c])
+    }
+    PF_MIX_EXP_POLY(G)
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        if (TWO_ACC && (c & 1))
+            lp1 = fma(tjs[c], P[c], lp1);
+        else
+            lp0 = fma(tjs[c], P[c], lp0);
+    }
+}
+
+// e = squared distance >= 0 (or NaN), clamped in place like mix_exp_accumulate: 7 FP64 + 5 other per component
+template <int G>
+__device__ __forceinline__ void mix_exp_accumulate_e(double (&e)[G], double& lp0, double& lp1, unsigned tab_l) {
+    double g[G], tjs[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        e[c] = __hiloint2double(min(__double2hiint(e[c]), kExpArgClampHi), __double2loint(e[c]));
+        const double t = fma(e[c], kNegHalfLog2e, kRintMagicRep);
+        g[c] = fma(e[c], kNegHalfLog2e, -(t - kRintMagicRep));
+        PF_MIX_EXP_CORE(t, tjs[c])
+    }
+    PF_MIX_EXP_POLY(G)
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        if (c & 1)
+            lp1 = fma(tjs[c], P[c], lp1);
+        else
+            lp0 = fma(tjs[c], P[c], lp0);
+    }
+}
+
+// log x = n ln 2 + (log c_j + log1p(r)): returns the bracket, adds n to `nacc` (the caller adds nacc ln 2 once per tile:
+// log_n_times_ln2).  x must be a positive normal number.  Its table (g_log_mid, filled by the host) has the MIDPOINT
+// of every mantissa interval as c_j -- also for the two intervals next to 1, which g_log_adj pins to c = 1 so that
+// log(1) = 0 exactly: |r| <= 2^-9 everywhere (with c = 1, r reaches 2^-8 and r^5/5 = 1.8e-13); log(1) comes out as
+// ~1e-17 instead of 0, which a sum over rows does not see.  Same addressing and same doubling of 1/c_j for
+// j >= kLogTabFirstHalf as log_pos_fast_k.
+__device__ __align__(16) double g_log_mid[512];
+constexpr double kLogC3 = 0.33333325386047363281;  // 0x3FD5555500000000 ~ 1/3 (its term is <= 2.5e-9: error 6e-16)
+__device__ __forceinline__ double log_pos_acc(double x, unsigned ltab_s, int& nacc) {
+    const int hi = __double2hiint(x);
+    const int A = hi + ((0x00100000 - (kLogTabFirstHalf << 12)) - 0x3FF00000);
+    nacc += A >> 20;
+    const double m = __hiloint2double(hi - (A & (int) 0xFFF00000), __double2loint(x));
+    double2 t;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(ltab_s + ((unsigned) (hi >> 8) & 0xFF0u)));
+    const double r = fma(m, t.x, -1.0);
+    double p = fma(-0.25, r, kLogC3);
+    p = fma(p, r, -0.5);
+    const double l1p = fma(r * r, p, r);
+    return t.y + l1p;
+}
+__device__ __forceinline__ double log_n_times_ln2(int nacc, double rest) {
+    const double nd = (double) nacc;
+    return fma(nd, kLn2Head, fma(nd, kLn2Tail, rest));  // |nacc| < 2^21: nd * kLn2Head is exact
 }
 
 template <int G>

@@ -37,6 +37,27 @@ namespace pf {
 #ifndef PF_PW_WARPS
 #define PF_PW_WARPS 8
 #endif
+// Tuning knobs of the FP64 mixture loops, with the measurements behind the defaults (N = 1e8, K = 8, d = 2, one B200;
+// ms per step at B = 8 / 1 / 32).  The loop is bound by REGISTERS, not by instruction count: 16 warps per SM leave 128
+// registers per thread, the theta-derived constants of the factored form take 48 of them, and every row in flight ~20
+// more, so fewer rows per iteration and fewer resident constants schedule better (ncu: short-scoreboard and fixed-latency
+// stalls at the consumers of the table reads fall from 2.9 + 2.8 to ~1 warp per issue slot):
+//   rows per iteration 4, A_k and B_k in registers, two partial sums      5.90 / 0.995 / 21.9
+//   rows per iteration 4, A_k re-read from shared memory per row          5.44 / 0.965
+//   ... and a single accumulation chain                                    5.35 / 0.950
+//   rows per iteration 2, A_k re-read, single chain  (the default)         5.24 / 0.927 / 19.7
+//   rows per iteration 3                                                   5.21 / 0.941 / 19.6
+//   rows per iteration 1                                                   6.67 / 0.989 / 26.0
+//   A_k and B_k both re-read (rows 2)                                      5.24 / 0.927 / 19.7
+#ifndef PF_MIX_RB
+#define PF_MIX_RB 2       // rows per iteration of the mixture loops
+#endif
+#ifndef PF_MIX_RELOAD
+#define PF_MIX_RELOAD 1   // factored form: 0 = theta-derived constants wherever the compiler puts them (registers),
+#endif                    // 1 = A_k re-read from shared memory for every row, 2 = A_k and B_k
+#ifndef PF_MIX_TWO_ACC
+#define PF_MIX_TWO_ACC 0  // factored mixture form: two partial sums per row (1) or a single accumulation chain (0)
+#endif
 constexpr int PW_CONSUMER_WARPS = PF_PW_WARPS;  // 8 warps = 256 threads: two CTAs per SM fit at up to 128 registers
 constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
 // PF_PW_FOLD: no dedicated producer warp -- lane 0 of consumer warp 0 issues the TMA copies between its rows.
@@ -49,11 +70,14 @@ constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
 #endif
 constexpr bool PW_FOLD = PF_PW_FOLD != 0;
 constexpr int PW_THREADS = PW_CONSUMERS + (PW_FOLD ? 0 : 32);  // + one producer warp
-constexpr int PW_STAGES = 4;
+#ifndef PF_PW_STAGES
+#define PF_PW_STAGES 3  // 16 KB tiles in flight per CTA (a tile is ~20 us of mixture work, its copy ~2 us)
+#endif
+constexpr int PW_STAGES = PF_PW_STAGES;
 constexpr int PW_TILE_BYTES = 16384;
 constexpr int PW_STAGE_BYTES = PW_TILE_BYTES + 32;  // room for the 16-byte aligned copy window
-constexpr int PW_RED_BUFS = 4;  // == PW_STAGES: a warp can never lead the owner warp by more than 3 tiles
-constexpr int PW_RED_DOUBLES = PW_RED_BUFS * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+constexpr int PW_RED_BUFS = 4;  // >= PW_STAGES: a warp can never lead the owner warp by more than PW_STAGES - 1 tiles
+static_assert(PW_RED_BUFS >= PW_STAGES, "tile-total buffers rotate at least as slowly as the stages");
 constexpr int PW_BAR_TILE0 = 1;  // named barriers 1..4: per-tile partials ready; 5: CTA-wide among consumers
 constexpr int PW_BAR_ALL = 5;
 constexpr double kLog2Pi = 1.837877066409345483560659472810;  // normalsampler.hh:24-26
@@ -86,6 +110,11 @@ __device__ __forceinline__ void load_row(const unsigned char* p, CT (&x)[DIM]) {
 // ---------------------------------------------------------------------------------------------
 // Model policies
 // ---------------------------------------------------------------------------------------------
+// Per-lane state a model carries through the rows of one tile besides its sums (see pw_main)
+struct NoRowState {
+    __device__ __forceinline__ void reset() {}
+};
+
 // Gaussian target.  theta = D means + packed lower-triangular covariance (normaltheta.hh:81-87).
 // prepare() of the reference (normalsampler.hh:87-113): identity covariance -> scale = -D log(2pi)/2;
 // otherwise LU-invert the covariance, scale = -(D log 2pi + log det)/2, and evaluate() uses the
@@ -95,8 +124,10 @@ struct NormalModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = true;
     static constexpr bool HAS_REDO = false;
+    static constexpr bool HAS_FIXUP = false;
     static constexpr bool THETA_IN_SMEM = false;
     using CT = typename ComputeOf<T>::type;
+    using RowState = NoRowState;
     struct Node {
         CT mu[D];
         CT w[GENERAL ? D * (D + 1) / 2 : 1];  // upper triangle of Winv, row-major, off-diagonals doubled
@@ -187,14 +218,36 @@ __host__ __device__ constexpr unsigned theta_smem_stride(unsigned theta_len) {
     return s;
 }
 
-template <int K, int D, typename T>
+// FACT = false: the clamped squared-distance form (any theta, any data; slow path for rows out of range).
+// FACT = true (FP64 only): the factored form  ln sum_k 2^(A_k + B_k.x) - |x|^2/2  of pf_math.cuh, chosen by the kernel
+// itself when every node's theta passes the range test against the data set's bounding box (pw_stage_theta).
+template <int K, int D, typename T, bool FACT = false>
 struct MixtureModel {
     static constexpr int DIM = D;
     static constexpr bool ITEM1 = false;
     static constexpr bool THETA_IN_SMEM = true;
-    static constexpr bool HAS_REDO = true;
     using CT = typename ComputeOf<T>::type;
-    static constexpr bool BIG_EXP_TABLE = sizeof(CT) == 8;  // FP64: 2048-entry table + mix_exp_accumulate
+    static constexpr bool BIG_EXP_TABLE = sizeof(CT) == 8;  // FP64: 2048-entry table + mix_exp_accumulate_*
+    static constexpr bool FACTORED = FACT && BIG_EXP_TABLE;
+    static constexpr bool HAS_REDO = !FACTORED;
+    static constexpr bool HAS_FIXUP = BIG_EXP_TABLE;       // n ln 2 (and -|x|^2/2) added once per tile
+    static constexpr int NCOMP = K;
+    static constexpr unsigned RB = BIG_EXP_TABLE ? PF_MIX_RB : 4;  // rows per loop iteration (FP32: MUFU-bound, 4 is best)
+    using Factored = MixtureModel<K, D, T, true>;           // the variant pw_frontier_body may switch to
+    // doubles staged per node: theta as it is, or [K][D] B then [K] A
+    static __host__ __device__ constexpr unsigned staged_len(unsigned theta_len) {
+        return FACTORED ? theta_len + K : theta_len;
+    }
+    struct RowState {
+        unsigned redo;  // slow_path_accumulate() key, tested once per tile
+        int nacc;       // sum of the rows' binary exponents (log_pos_acc)
+        double xsq;     // sum of the rows' |x|^2 (factored form)
+        __device__ __forceinline__ void reset() {
+            redo = 0u;
+            nacc = 0;
+            xsq = 0.0;
+        }
+    };
     struct Node {
         const CT* th;
         unsigned tab_s;       // shared-memory ADDRESS of the exp table (FP64: 2048 adjusted entries; float: unused)
@@ -203,7 +256,8 @@ struct MixtureModel {
     };
     static __device__ void load(Node& nd, const CT* th_smem, unsigned, const double* tab, const double2* ltab) {
         nd.th = th_smem;
-        nd.tab_s = smem_u32(tab);
+        // FP64: this lane's copy of the replicated table (bank pair = lane mod 16: every lookup is conflict free)
+        nd.tab_s = smem_u32(tab) + (BIG_EXP_TABLE ? (threadIdx.x & (kExpRepCopies - 1)) * 8u : 0u);
         nd.ltab_s = smem_u32(ltab);
         nd.ltab = ltab;
     }
@@ -220,15 +274,45 @@ struct MixtureModel {
         }
         return (CT) log(lp);
     }
-    static __device__ __forceinline__ CT mix_sum(const Node& nd, const CT (&x)[D]) {
-        // exp chains kept in flight per lane (bounded by the registers the row operands need)
+    // exp chains kept in flight per lane (bounded by the registers the row operands need)
 #ifdef PF_MIX_G
-        constexpr int GMAX = PF_MIX_G;
+    static constexpr int GMAX = PF_MIX_G;
 #else
-        constexpr int GMAX = D <= 2 ? 8 : (D <= 4 ? 4 : 2);
+    static constexpr int GMAX = D <= 2 ? 8 : (D <= 4 ? 4 : 2);
 #endif
-        constexpr int G = (K % GMAX == 0) ? GMAX : ((K % 2 == 0) ? 2 : 1);
-        if constexpr (BIG_EXP_TABLE) {
+    static constexpr int G = (K % GMAX == 0) ? GMAX : ((K % 2 == 0) ? 2 : 1);
+
+    static __device__ __forceinline__ CT mix_sum(const Node& nd, const CT (&x)[D]) {
+        if constexpr (FACTORED) {
+            double lp0 = 0.0, lp1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < K; k0 += G) {
+                double z[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    double b[D], a;
+#if PF_MIX_RELOAD >= 2
+                    static_assert(D % 2 == 0, "reload variant: even d");
+#pragma unroll
+                    for (int j = 0; j < D; j += 2)
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b[j]), "=d"(b[j + 1])
+                                     : "r"(smem_u32(nd.th) + (unsigned) (((k0 + g) * D + j) * 8)));
+#else
+                    load_row<double, D, double>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), b);
+#endif
+#if PF_MIX_RELOAD >= 1
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(smem_u32(nd.th) + (unsigned) ((K * D + k0 + g) * 8)));
+#else
+                    a = nd.th[K * D + k0 + g];
+#endif
+                    z[g] = fma(b[0], x[0], a);
+#pragma unroll
+                    for (int j = 1; j < D; ++j) z[g] = fma(b[j], x[j], z[g]);
+                }
+                mix_exp_accumulate_z<G, PF_MIX_TWO_ACC != 0>(z, lp0, lp1, nd.tab_s);
+            }
+            return PF_MIX_TWO_ACC ? lp0 + lp1 : lp0;
+        } else if constexpr (BIG_EXP_TABLE) {
             double lp0 = 0.0, lp1 = 0.0;
 #pragma unroll
             for (int k0 = 0; k0 < K; k0 += G) {
@@ -245,53 +329,74 @@ struct MixtureModel {
                         e[g] = fma(t, t, e[g]);
                     }
                 }
-                mix_exp_accumulate<G>(e, lp0, lp1, nd.tab_s);
+                mix_exp_accumulate_e<G>(e, lp0, lp1, nd.tab_s);
             }
             return (CT) (lp0 + lp1);
-        }
-        CT lp = 0;
+        } else {
+            CT lp = 0;
 #pragma unroll
-        for (int k0 = 0; k0 < K; k0 += G) {
-            CT e[G], v[G];
+            for (int k0 = 0; k0 < K; k0 += G) {
+                CT e[G], v[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                CT th[D];
-                load_row<CT, D, CT>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), th);
-                e[g] = 0;
+                for (int g = 0; g < G; ++g) {
+                    CT th[D];
+                    load_row<CT, D, CT>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), th);
+                    e[g] = 0;
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const CT t = th[j] - x[j];
-                    e[g] = fma(t, t, e[g]);
+                    for (int j = 0; j < D; ++j) {
+                        const CT t = th[j] - x[j];
+                        e[g] = fma(t, t, e[g]);
+                    }
                 }
+                exp_neg_half_fast_batch_s<G>(e, v, nd.tab_s);
+#pragma unroll
+                for (int w = 1; w < G; w *= 2)  // pairwise: depth log2(G) instead of G dependent adds
+#pragma unroll
+                    for (int g = 0; g + w < G; g += 2 * w) v[g] += v[g + w];
+                lp += v[0];
             }
-            exp_neg_half_fast_batch_s<G>(e, v, nd.tab_s);
-#pragma unroll
-            for (int w = 1; w < G; w *= 2)  // pairwise: depth log2(G) instead of G dependent adds
-#pragma unroll
-                for (int g = 0; g + w < G; g += 2 * w) v[g] += v[g + w];
-            lp += v[0];
+            return lp;
         }
-        return lp;
     }
-    // Hot loop: branch free.  A row whose sum left the fast path's range (every component ~40 sigma away, or
-    // non-finite input) contributes garbage here and raises `redo`; the caller then DISCARDS this lane's sums of
+    // Hot loop: branch free.  Clamped form: a row whose sum left the fast path's range (every component ~40 sigma away,
+    // or non-finite input) contributes garbage here and raises `st.redo`; the caller then DISCARDS this lane's sums of
     // the tile and re-walks its rows with rowlp_redo (fast value, or the library for the rows out of range), so
     // the library call -- whose ABI clobbers the uniform registers holding the polynomial constants -- and the
-    // masking selects stay out of the loop the FP64 pipe lives in.
-    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], unsigned& redo) {
+    // masking selects stay out of the loop the FP64 pipe lives in.  Factored form: nothing can leave the range.
+    // FP64: the value returned lacks n ln 2 (and -|x|^2/2): tile_fixup() adds those once per tile.
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], RowState& st) {
         const CT lp = mix_sum(nd, x);
-        slow_path_accumulate(redo, lp);  // the value is NOT masked (see above)
-        if constexpr (BIG_EXP_TABLE)
-            return log_pos_fast_k(lp, nd.ltab_s);
-        else
-            return log_pos_fast(lp, nd.ltab);
+        if constexpr (FACTORED) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) st.xsq = fma(x[j], x[j], st.xsq);
+            return log_pos_acc(lp, nd.ltab_s, st.nacc);
+        } else {
+            slow_path_accumulate(st.redo, lp);  // the value is NOT masked (see above)
+            if constexpr (BIG_EXP_TABLE)
+                return log_pos_acc(lp, nd.ltab_s, st.nacc);
+            else
+                return log_pos_fast(lp, nd.ltab);
+        }
     }
+    static __device__ __forceinline__ bool needs_redo(const RowState& st) {
+        if constexpr (HAS_REDO) return acc_needs_slow_path(st.redo);
+        return false;
+    }
+    static __device__ __forceinline__ void tile_fixup(const RowState& st, double& acc) {
+        if constexpr (FACTORED)
+            acc = log_n_times_ln2(st.nacc, fma(-0.5, st.xsq, acc));
+        else if constexpr (BIG_EXP_TABLE)
+            acc = log_n_times_ln2(st.nacc, acc);
+    }
+    // complete value of one row (cold path)
     static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
         const CT lp = mix_sum(nd, x);
         if (needs_slow_path(lp)) return slow(nd.th, x);
-        if constexpr (BIG_EXP_TABLE)
-            return log_pos_fast_k(lp, nd.ltab_s);
-        else
+        if constexpr (BIG_EXP_TABLE) {
+            int n = 0;
+            const double rest = log_pos_acc(lp, nd.ltab_s, n);
+            return log_n_times_ln2(n, rest);
+        } else
             return log_pos_fast(lp, nd.ltab);
     }
 };
@@ -304,7 +409,17 @@ struct MixtureModelRT {
     static constexpr bool ITEM1 = false;
     static constexpr bool THETA_IN_SMEM = true;
     static constexpr bool HAS_REDO = true;
+    static constexpr bool HAS_FIXUP = false;
+    static constexpr bool BIG_EXP_TABLE = false;
+    static constexpr bool FACTORED = false;
+    static constexpr unsigned RB = 4;
     using CT = typename ComputeOf<T>::type;
+    static __host__ __device__ constexpr unsigned staged_len(unsigned theta_len) { return theta_len; }
+    struct RowState {
+        unsigned redo;
+        __device__ __forceinline__ void reset() { redo = 0u; }
+    };
+    static __device__ __forceinline__ bool needs_redo(const RowState& st) { return acc_needs_slow_path(st.redo); }
     struct Node {
         const CT* th;
         const double* tab;
@@ -330,9 +445,9 @@ struct MixtureModelRT {
         }
         return lp;
     }
-    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], unsigned& redo) {
+    static __device__ __forceinline__ CT rowlp_fast(const Node& nd, const CT (&x)[D], RowState& st) {
         const CT lp = mix_sum(nd, x);
-        slow_path_accumulate(redo, lp);
+        slow_path_accumulate(st.redo, lp);
         return log_pos_fast(lp, nd.ltab);
     }
     static __device__ CT rowlp_redo(const Node& nd, const CT (&x)[D]) {
@@ -389,9 +504,12 @@ struct BigExpTable<M, std::enable_if_t<M::BIG_EXP_TABLE>> { static constexpr boo
 template <class M>
 __host__ __device__ constexpr bool big_exp_table() { return BigExpTable<M>::value; }
 
-template <class M>
+// per-warp slots of the block reductions: [buffer][warp][32 * NPL nodes]; the finalize step reuses the area as scratch
+// (finalize_items: 2 doubles per thread; peer_allreduce: 2 * kMaxNodesPerPass)
+template <class M, int NPL>
 __host__ __device__ constexpr int pw_red_doubles() {
-    return (M::ITEM1 ? 2 : PW_RED_BUFS) * PW_CONSUMER_WARPS * kMaxNodesPerPass;
+    constexpr int n = (M::ITEM1 ? 2 : PW_RED_BUFS) * PW_CONSUMER_WARPS * 32 * NPL;
+    return n > 2 * PW_CONSUMERS ? n : 2 * PW_CONSUMERS;
 }
 
 template <class M, int NPL>
@@ -418,6 +536,37 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pw_frontier_kernel1(const __gri
     pw_frontier_body<M, T, NPL>(a);
 }
 
+// what pw_frontier_body carves out of shared memory and hands to pw_main
+struct PwShared {
+    unsigned char* stage_base;
+    double* red;
+    uint64_t *full, *empty;
+    int* flag;
+    void* th_smem;
+    const double* exp2_tab;
+    const double2* log_tab;
+    unsigned long long r0, r1;
+    const unsigned long long* theta_nan;
+};
+
+template <class M, class = void>
+struct FactoredOf { using type = void; };
+template <class M>
+struct FactoredOf<M, std::enable_if_t<M::BIG_EXP_TABLE && !M::FACTORED>> { using type = typename M::Factored; };
+
+// doubles of shared memory per staged node (the larger of the two layouts a model may use)
+template <class M>
+__host__ __device__ constexpr unsigned pw_staged_len(unsigned theta_len) {
+    if constexpr (M::THETA_IN_SMEM) {
+        if constexpr (!std::is_void<typename FactoredOf<M>::type>::value)
+            return FactoredOf<M>::type::staged_len(theta_len);
+    }
+    return theta_len;
+}
+
+template <class M, typename T, int NPL>
+__device__ __forceinline__ void pw_main(const PointwiseArgs& a, const PwShared& sh);
+
 template <class M, typename T, int NPL>
 __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     using CT = typename M::CT;
@@ -426,34 +575,158 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
     constexpr unsigned TILE_ROWS = PW_TILE_BYTES / RB_BYTES;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* stage_base = smem;
-    double* red = reinterpret_cast<double*>(smem + PW_STAGES * PW_STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + pw_red_doubles<M>());
-    uint64_t* empty = full + PW_STAGES;
-    int* flag = reinterpret_cast<int*>(empty + PW_STAGES);
-    CT* th_smem = reinterpret_cast<CT*>(reinterpret_cast<unsigned char*>(flag) + 16);  // 16-byte aligned
+    PwShared sh;
+    sh.stage_base = smem;
+    sh.red = reinterpret_cast<double*>(smem + PW_STAGES * PW_STAGE_BYTES);
+    sh.full = reinterpret_cast<uint64_t*>(sh.red + pw_red_doubles<M, NPL>());
+    sh.empty = sh.full + PW_STAGES;
+    sh.flag = reinterpret_cast<int*>(sh.empty + PW_STAGES);
+    CT* th_smem = reinterpret_cast<CT*>(reinterpret_cast<unsigned char*>(sh.flag) + 16);  // 16-byte aligned
+    sh.th_smem = th_smem;
+    sh.exp2_tab = nullptr;
+    sh.log_tab = nullptr;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned long long r0 = a.row_begin + (unsigned long long) blockIdx.x * a.rows_per_cta;
     if (r0 > a.row_end) r0 = a.row_end;
     unsigned long long r1 = r0 + a.rows_per_cta;
     if (r1 > a.row_end) r1 = a.row_end;
+    sh.r0 = r0;
+    sh.r1 = r1;
 
     __shared__ unsigned long long theta_nan;  // bit b: node b has a NaN in its theta (see mix_exp_accumulate)
     __shared__ uint64_t tabbar;               // completion of the exp / log table copies (mixture, FP64)
+    __shared__ int not_factorable;            // some node's theta fails the range test of the factored form
+    sh.theta_nan = &theta_nan;
     const bool tr0 = tid == 0 && blockIdx.x == 0;
     trace_mark(a.trace, 0, 0, tr0);
     trace_cta(a.trace, 0, tid == 0);
     if (tid == 0) {
         for (int s = 0; s < PW_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], PW_CONSUMER_WARPS);
+            mbar_init(&sh.full[s], 1);
+            mbar_init(&sh.empty[s], PW_CONSUMER_WARPS);
         }
         mbar_init(&tabbar, 1);
         fence_barrier_init();
         theta_nan = 0ull;
+        not_factorable = 0;
     }
     __syncthreads();
+
+    if (!PW_FOLD && warp == PW_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS, 0ull};
+            unsigned long long t0, t1;
+            unsigned t = 0;
+            while (it.next(t0, t1)) {
+                const unsigned s = t % PW_STAGES;
+                if (t >= PW_STAGES) mbar_wait(&sh.empty[s], ((t / PW_STAGES) - 1) & 1);
+                const unsigned long long b0 = t0 * RB_BYTES, b1 = t1 * RB_BYTES;
+                const unsigned long long w0 = b0 & ~15ull, w1 = (b1 + 15ull) & ~15ull;
+                const unsigned bytes = (unsigned) (w1 - w0);
+                mbar_arrive_expect_tx(&sh.full[s], bytes);
+                bulk_g2s(sh.stage_base + s * PW_STAGE_BYTES, static_cast<const unsigned char*>(a.data) + w0, bytes,
+                         &sh.full[s]);
+                ++t;
+            }
+        }
+        return;
+    }
+
+    if constexpr (M::THETA_IN_SMEM) {
+        // thetas: device memory, or the kernel parameters themselves (__grid_constant__: their address may be taken)
+        const double* const theta = a.theta_inline_n ? a.theta_inline : a.theta;
+        const unsigned B = a.B;
+        // The 2^(j/256) table sits at a shared-memory ADDRESS aligned to its own size (exp_neg_half_fast_batch_s ORs
+        // the entry offset into it).  __align__ only aligns the offset behind the 1 KB the hardware reserves at
+        // the start of the window, so the aligned 2 KB are picked out of a 4 KB array by hand.
+        constexpr bool BIG = big_exp_table<M>();
+        __shared__ __align__(128) double exp2_raw[BIG ? kExpRepSize * kExpRepCopies : 2 * kExp2TabSize];
+        __shared__ __align__(16) double2 log_tab[256];
+        constexpr unsigned kTabBytes = kExp2TabSize * 8;
+        const unsigned raw_s = smem_u32(exp2_raw);
+        double* const exp2_tab = BIG ? exp2_raw : exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
+        sh.exp2_tab = exp2_tab;
+        sh.log_tab = log_tab;
+        if constexpr (BIG) {
+            // 32 KB (256 entries x 16 copies) + 4 KB by two TMA bulk copies
+            if (tid == 0) {
+                constexpr unsigned kRepBytes = (unsigned) (sizeof(double) * kExpRepSize * kExpRepCopies);
+                mbar_arrive_expect_tx(&tabbar, kRepBytes + (unsigned) (sizeof(double2) * 256));
+                bulk_g2s(exp2_tab, g_exp2_rep, kRepBytes, &tabbar);
+                bulk_g2s(log_tab, g_log_mid, (unsigned) (sizeof(double2) * 256), &tabbar);
+            }
+        } else {
+            for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
+            for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
+        }
+        using MF = typename FactoredOf<M>::type;
+        [[maybe_unused]] bool factored = false;
+        if constexpr (!std::is_void<MF>::value && NPL == 1) {
+            // Factored layout per node: [K][D] B = log2(e) theta, then [K] A = -log2(e)/2 |theta_k|^2 -- and the range
+            // test that licenses it: |A_k| + sum_j |B_kj| max|x_j| <= kFactoredLimit for every component of every node
+            // (a NaN / inf anywhere fails the comparison).  Every CTA reaches the same verdict from the same inputs.
+            constexpr unsigned KC = MF::NCOMP;
+            const unsigned stride = theta_smem_stride<double>(MF::staged_len(a.theta_len));
+            bool bad = false;
+            for (unsigned i = tid; i < B * KC; i += PW_CONSUMERS) {
+                const unsigned node = i / KC, k = i - node * KC;
+                const double* th = theta + (size_t) node * a.theta_len + k * DIM;
+                double* dst = reinterpret_cast<double*>(th_smem) + node * stride;
+                double nrm = 0.0, bound = 0.0;
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                    const double v = th[j], bj = v * kLog2e;
+                    dst[k * DIM + j] = bj;
+                    nrm = fma(v, v, nrm);
+                    bound = fma(fabs(bj), a.xmax[j], bound);
+                }
+                const double A = nrm * kNegHalfLog2e;
+                dst[KC * DIM + k] = A;
+                bad |= !(fabs(A) + bound <= kFactoredLimit);
+            }
+            if (bad) atomicOr(&not_factorable, 1);
+            named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
+            factored = not_factorable == 0;
+        }
+        if (!factored) {
+            const unsigned stride = theta_smem_stride<CT>(a.theta_len);
+            for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
+                const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
+                const double v = theta[i];
+                th_smem[node * stride + j] = (CT) v;
+                if constexpr (BIG)
+                    if (v != v) atomicOr(&theta_nan, 1ull << node);
+            }
+            named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
+        }
+        if constexpr (BIG) mbar_wait(&tabbar, 0);
+        if (a.trace != nullptr && tr0) a.trace[6] = factored ? 1ull : 2ull;  // diagnostics: which form scores this call
+        if constexpr (!std::is_void<MF>::value && NPL == 1) {
+            if (factored) {
+                pw_main<MF, T, NPL>(a, sh);
+                return;
+            }
+        }
+    }
+    pw_main<M, T, NPL>(a, sh);
+}
+
+template <class M, typename T, int NPL>
+__device__ __forceinline__ void pw_main(const PointwiseArgs& a, const PwShared& sh) {
+    using CT = typename M::CT;
+    constexpr int DIM = M::DIM;
+    constexpr int RB_BYTES = DIM * (int) sizeof(T);
+    constexpr unsigned TILE_ROWS = PW_TILE_BYTES / RB_BYTES;
+    unsigned char* const stage_base = sh.stage_base;
+    double* const red = sh.red;
+    uint64_t* const full = sh.full;
+    uint64_t* const empty = sh.empty;
+    int* const flag = sh.flag;
+    const unsigned long long r0 = sh.r0, r1 = sh.r1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tr0 = tid == 0 && blockIdx.x == 0;
 
     // one tile's copy: rows [t0, t1) -> stage s, completion counted on full[s]
     auto issue_tile = [&](unsigned long long t0, unsigned long long t1, unsigned s) {
@@ -464,31 +737,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         bulk_g2s(stage_base + s * PW_STAGE_BYTES, static_cast<const unsigned char*>(a.data) + w0, bytes, &full[s]);
     };
 
-    if (!PW_FOLD && warp == PW_CONSUMER_WARPS) {
-        // ------------------------------------------------------------------ producer warp
-        if (lane == 0) {
-            TileIter it{r0, r1, a.item_rows, a.row_end, TILE_ROWS, 0ull};
-            unsigned long long t0, t1;
-            unsigned t = 0;
-            while (it.next(t0, t1)) {
-                const unsigned s = t % PW_STAGES;
-                if (t >= PW_STAGES) mbar_wait(&empty[s], ((t / PW_STAGES) - 1) & 1);
-                const unsigned long long b0 = t0 * RB_BYTES, b1 = t1 * RB_BYTES;
-                const unsigned long long w0 = b0 & ~15ull, w1 = (b1 + 15ull) & ~15ull;
-                const unsigned bytes = (unsigned) (w1 - w0);
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_g2s(stage_base + s * PW_STAGE_BYTES, static_cast<const unsigned char*>(a.data) + w0, bytes,
-                         &full[s]);
-                ++t;
-            }
-        }
-        return;
-    }
-
     // ---------------------------------------------------------------------- consumer warps
     const unsigned B = a.B;
-    // thetas: device memory, or the kernel parameters themselves (__grid_constant__: their address may be taken)
-    const double* const theta = a.theta_inline_n ? a.theta_inline : a.theta;
     unsigned NB = 32;  // node lanes (power of two >= min(B, 32))
     if (B < 32) {
         NB = 1;
@@ -500,43 +750,15 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 
     typename M::Node nd[NPL];
     if constexpr (M::THETA_IN_SMEM) {
-        // The 2^(j/256) table sits at a shared-memory ADDRESS aligned to its own size (exp_neg_half_fast_batch_s ORs
-        // the entry offset into it).  __align__ only aligns the offset behind the 1 KB the hardware reserves at
-        // the start of the window, so the aligned 2 KB are picked out of a 4 KB array by hand.
-        constexpr bool BIG = big_exp_table<M>();
-        __shared__ __align__(16) double exp2_raw[BIG ? kExpBigSize : 2 * kExp2TabSize];
-        __shared__ __align__(16) double2 log_tab[256];
-        constexpr unsigned kTabBytes = kExp2TabSize * 8;
-        const unsigned raw_s = smem_u32(exp2_raw);
-        double* const exp2_tab = BIG ? exp2_raw : exp2_raw + ((((raw_s + kTabBytes - 1) & ~(kTabBytes - 1)) - raw_s) >> 3);
-        if constexpr (BIG) {
-            // 16 KB + 4 KB by two TMA bulk copies (20 us -> 7 us of fixed cost per call against per-thread loads)
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&tabbar, (unsigned) (sizeof(double) * kExpBigSize + sizeof(double2) * 256));
-                bulk_g2s(exp2_tab, g_exp2_big, (unsigned) (sizeof(double) * kExpBigSize), &tabbar);
-                bulk_g2s(log_tab, g_log_adj, (unsigned) (sizeof(double2) * 256), &tabbar);
-            }
-        } else {
-            for (int i = tid; i < kExp2TabSize; i += PW_CONSUMERS) exp2_tab[i] = kExp2Tab[i];
-            for (int i = tid; i < 256; i += PW_CONSUMERS) log_tab[i] = make_double2(kLogTab[2 * i], kLogTab[2 * i + 1]);
-        }
-        const unsigned stride = theta_smem_stride<CT>(a.theta_len);
-        for (unsigned i = tid; i < B * a.theta_len; i += PW_CONSUMERS) {
-            const unsigned node = i / a.theta_len, j = i - node * a.theta_len;
-            const double v = theta[i];
-            th_smem[node * stride + j] = (CT) v;
-            if constexpr (BIG)
-                if (v != v) atomicOr(&theta_nan, 1ull << node);
-        }
-        named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
-        if constexpr (BIG) mbar_wait(&tabbar, 0);
+        const unsigned stride = theta_smem_stride<CT>(M::staged_len(a.theta_len));
 #pragma unroll
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
             if (node >= B) node = B - 1;  // idle lanes shadow the last node; their sums are dropped
-            M::load(nd[n], th_smem + node * stride, a.K, exp2_tab, log_tab);
+            M::load(nd[n], reinterpret_cast<const CT*>(sh.th_smem) + node * stride, a.K, sh.exp2_tab, sh.log_tab);
         }
     } else {
+        const double* const theta = a.theta_inline_n ? a.theta_inline : a.theta;
 #pragma unroll
         for (int n = 0; n < NPL; ++n) {
             unsigned node = nb + 32 * n;
@@ -600,7 +822,9 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         // four; with one node and 32 point-lanes (B = 1) a lane has only four rows of a tile and two at a time are
         // best; with two nodes per lane batching only spills.)
         unsigned j = slot;
-        [[maybe_unused]] unsigned redo = 0u;  // slow_path_accumulate() key, tested once per tile
+        typename M::RowState st[NPL];  // per-tile lane state besides the sums (slow-path key, exponent sum, |x|^2 sum)
+#pragma unroll
+        for (int n = 0; n < NPL; ++n) st[n].reset();
         auto batch_rows = [&](auto rb_tag) {
             constexpr unsigned RB = decltype(rb_tag)::value;
             for (; j + (RB - 1) * nslots < nrows; j += RB * nslots) {
@@ -612,8 +836,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 #pragma unroll
                     for (int n = 0; n < NPL; ++n) {
                         double v;
-                        if constexpr (M::HAS_REDO)
-                            v = (double) M::rowlp_fast(nd[n], x[u], redo);
+                        if constexpr (M::HAS_REDO || M::HAS_FIXUP)
+                            v = (double) M::rowlp_fast(nd[n], x[u], st[n]);
                         else
                             v = (double) M::rowlp(nd[n], x[u]);
                         accS[n] += v;
@@ -624,8 +848,10 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         if constexpr (M::ITEM1)
             batch_rows(std::integral_constant<unsigned, 4>{});
         else if constexpr (NPL == 1) {
-            if (PL <= 8) batch_rows(std::integral_constant<unsigned, 4>{});
-            batch_rows(std::integral_constant<unsigned, 2>{});
+            if constexpr (M::RB >= 4)
+                if (PL <= 8) batch_rows(std::integral_constant<unsigned, 4>{});
+            if constexpr (M::RB == 3) batch_rows(std::integral_constant<unsigned, 3>{});
+            if constexpr (M::RB >= 2) batch_rows(std::integral_constant<unsigned, 2>{});
         }
         for (; j < nrows; j += nslots) {
             CT x[DIM];
@@ -633,8 +859,8 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
                 double v;
-                if constexpr (M::HAS_REDO)
-                    v = (double) M::rowlp_fast(nd[n], x, redo);
+                if constexpr (M::HAS_REDO || M::HAS_FIXUP)
+                    v = (double) M::rowlp_fast(nd[n], x, st[n]);
                 else
                     v = (double) M::rowlp(nd[n], x);
                 accS[n] += v;
@@ -643,7 +869,10 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
         }
         if (issue_pending) try_issue(t, true);
         if constexpr (M::HAS_REDO) {
-            if (acc_needs_slow_path(redo)) {  // cold: discard this lane's sums of the tile (they start at 0 per tile) and walk its rows again
+            bool again = false;
+#pragma unroll
+            for (int n = 0; n < NPL; ++n) again |= M::needs_redo(st[n]);
+            if (again) {  // cold: discard this lane's sums of the tile (they start at 0 per tile) and walk its rows again
 #pragma unroll
                 for (int n = 0; n < NPL; ++n) accS[n] = 0.0;
                 for (unsigned j2 = slot; j2 < nrows; j2 += nslots) {
@@ -652,7 +881,13 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
 #pragma unroll
                     for (int n = 0; n < NPL; ++n) accS[n] += (double) M::rowlp_redo(nd[n], x);
                 }
+#pragma unroll
+                for (int n = 0; n < NPL; ++n) st[n].reset();  // rowlp_redo returns complete values: nothing left for the fix-up
             }
+        }
+        if constexpr (M::HAS_FIXUP) {
+#pragma unroll
+            for (int n = 0; n < NPL; ++n) M::tile_fixup(st[n], accS[n]);
         }
         if constexpr (M::ITEM1) {
             __syncwarp();
@@ -663,13 +898,14 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             // warp(s) -- the ones holding threads tid < B -- WAIT on it, then fold the per-warp slots.  The
             // smem stage is released after the arrival, which bounds any warp's lead to 3 tiles, so a
             // buffer is never rewritten before the owners have read it.
-            double* r = red + (t & (PW_RED_BUFS - 1)) * (PW_CONSUMER_WARPS * kMaxNodesPerPass);
+            constexpr int RS = 32 * NPL;  // slot row stride
+            double* r = red + (t & (PW_RED_BUFS - 1)) * (PW_CONSUMER_WARPS * RS);
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
                 double v = accS[n];
                 accS[n] = 0.0;
                 for (unsigned m = 16; m >= NB; m >>= 1) v += shfl_xor_f64(v, m);
-                if (pl == 0) r[warp * kMaxNodesPerPass + nb + 32 * n] = v;
+                if (pl == 0) r[warp * RS + nb + 32 * n] = v;
             }
             const int bar = PW_BAR_TILE0 + (int) (t & (PW_RED_BUFS - 1));
             const bool owner_warp = (unsigned) (warp * 32) < B;
@@ -680,7 +916,7 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
             if ((unsigned) tid < B) {
                 double tot = 0.0;
 #pragma unroll
-                for (int w = 0; w < PW_CONSUMER_WARPS; ++w) tot += r[w * kMaxNodesPerPass + tid];
+                for (int w = 0; w < PW_CONSUMER_WARPS; ++w) tot += r[w * RS + tid];
                 own.add_tile(tot, t1, a.item_rows, a.row_end);
             }
             __syncwarp();  // owners have read the slots before this warp frees the stage
@@ -701,23 +937,23 @@ __device__ __forceinline__ void pw_frontier_body(const PointwiseArgs& a) {
                 q += shfl_xor_f64(q, m);
             }
             if (pl == 0) {
-                red[warp * kMaxNodesPerPass + nb + 32 * n] = v;
-                red[PW_CONSUMER_WARPS * kMaxNodesPerPass + warp * kMaxNodesPerPass + nb + 32 * n] = q;
+                red[warp * (32 * NPL) + nb + 32 * n] = v;
+                red[PW_CONSUMER_WARPS * (32 * NPL) + warp * (32 * NPL) + nb + 32 * n] = q;
             }
         }
         named_bar_sync(PW_BAR_ALL, PW_CONSUMERS);
         if ((unsigned) tid < B) {
 #pragma unroll
             for (int w = 0; w < PW_CONSUMER_WARPS; ++w) {
-                own.S += red[w * kMaxNodesPerPass + tid];
-                own.Q += red[PW_CONSUMER_WARPS * kMaxNodesPerPass + w * kMaxNodesPerPass + tid];
+                own.S += red[w * (32 * NPL) + tid];
+                own.Q += red[PW_CONSUMER_WARPS * (32 * NPL) + w * (32 * NPL) + tid];
             }
         }
     } else if ((unsigned) tid < B)
         own.finish(r0, r1, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows);
     if ((unsigned) tid < B) {
         if constexpr (big_exp_table<M>())
-            if ((theta_nan >> tid) & 1ull) own.S = own.Q = __longlong_as_double(0x7FF8000000000000ll);
+            if ((*sh.theta_nan >> tid) & 1ull) own.S = own.Q = __longlong_as_double(0x7FF8000000000000ll);
         own.store(rec, tid);
         __threadfence();
     }
@@ -861,10 +1097,14 @@ __global__ void debug_math_kernel(int which, const double* in, double* out, size
 // diagnostics for the mixture loop's own pair (mix_exp_accumulate / log_pos_fast_k): which = 5: exp(-x/2), 6: log(x)
 __global__ void debug_math_kernel_big(int which, const double* in, double* out, size_t n) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
-    __shared__ double tab[kExpBigSize];
+    __shared__ __align__(128) double tab[kExpRepSize * kExpRepCopies];  // (>= kExpBigSize)
     __shared__ __align__(16) double2 ltab[256];
-    for (int k = threadIdx.x; k < kExpBigSize; k += blockDim.x) tab[k] = g_exp2_big[k];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) ltab[k] = make_double2(g_log_adj[2 * k], g_log_adj[2 * k + 1]);
+    if (which >= 7)
+        for (int k = threadIdx.x; k < kExpRepSize * kExpRepCopies; k += blockDim.x) tab[k] = g_exp2_rep[k];
+    else
+        for (int k = threadIdx.x; k < kExpBigSize; k += blockDim.x) tab[k] = g_exp2_big[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x)
+        ltab[k] = which == 8 ? make_double2(g_log_mid[2 * k], g_log_mid[2 * k + 1]) : make_double2(g_log_adj[2 * k], g_log_adj[2 * k + 1]);
     __syncthreads();
     if (i >= n) return;
     double r;
@@ -872,6 +1112,18 @@ __global__ void debug_math_kernel_big(int which, const double* in, double* out, 
         double e[1] = {in[i]}, lp0 = 0.0, lp1 = 0.0;
         mix_exp_accumulate<1>(e, lp0, lp1, smem_u32(tab));
         r = lp0 + lp1;
+    } else if (which == 7) {  // the factored loop's exp: 2^z
+        double z[1] = {in[i]}, lp0 = 0.0, lp1 = 0.0;
+        mix_exp_accumulate_z<1, true>(z, lp0, lp1, smem_u32(tab) + (threadIdx.x & 15) * 8u);
+        r = lp0 + lp1;
+    } else if (which == 9) {  // the clamped loop's exp, degree 2: exp(-x/2)
+        double e[1] = {in[i]}, lp0 = 0.0, lp1 = 0.0;
+        mix_exp_accumulate_e<1>(e, lp0, lp1, smem_u32(tab) + (threadIdx.x & 15) * 8u);
+        r = lp0 + lp1;
+    } else if (which == 8) {  // log with the exponent accumulated apart
+        int n = 0;
+        const double rest = log_pos_acc(in[i], smem_u32(ltab), n);
+        r = log_n_times_ln2(n, rest);
     } else
         r = log_pos_fast_k(in[i], smem_u32(ltab));
     out[i] = r;
@@ -884,11 +1136,11 @@ namespace {
 
 constexpr size_t kPwSmemFixed = (size_t) PW_STAGES * PW_STAGE_BYTES + 2 * PW_STAGES * sizeof(uint64_t) + 32;
 
-template <class M>
+template <class M, int NPL>
 size_t pw_smem_bytes(unsigned theta_len, unsigned max_nodes) {
-    const size_t base = kPwSmemFixed + (size_t) pw_red_doubles<M>() * sizeof(double);
+    const size_t base = kPwSmemFixed + (size_t) pw_red_doubles<M, NPL>() * sizeof(double);
     if (!M::THETA_IN_SMEM) return base;
-    return base + (size_t) max_nodes * theta_smem_stride<typename M::CT>(theta_len) * sizeof(typename M::CT);
+    return base + (size_t) max_nodes * theta_smem_stride<typename M::CT>(pw_staged_len<M>(theta_len)) * sizeof(typename M::CT);
 }
 
 // g_exp2_big on the engine's device: B3 2^(j/2048) rounded from long double, (j << 9) subtracted from the high word
@@ -904,14 +1156,31 @@ int ensure_exp_table(Engine& e) {
         bits -= (unsigned long long) ((unsigned) j << 9) << 32;
         memcpy(&host_tab[j], &bits, 8);
     }
+    static double host_rep[kExpRepSize * kExpRepCopies];
+    for (int j = 0; j < kExpRepSize; ++j) {  // the kernels' table: B3 2^(j/256), high word - (j << 12), 16 copies side by side
+        const double v = (double) (kExp3B3 * exp2l((long double) j / kExpRepSize));
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        bits -= (unsigned long long) ((unsigned) j << 12) << 32;
+        for (int c = 0; c < kExpRepCopies; ++c) memcpy(&host_rep[j * kExpRepCopies + c], &bits, 8);
+    }
     static double host_log[512];
     if (cudaMemcpyFromSymbol(host_log, kLogTab, sizeof host_log) != cudaSuccess) {
         set_error("download of the log table failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
     for (int j = kLogTabFirstHalf; j < 256; ++j) host_log[2 * j] *= 2.0;  // see log_pos_fast_k
+    static double host_mid[512];  // log_pos_acc's table: {1/c_j (doubled in the upper half), -log of exactly that number}
+    for (int j = 0; j < 256; ++j) {
+        const long double c = 1.0L + ((long double) j + 0.5L) / 256.0L;
+        const double inv = (double) ((j >= kLogTabFirstHalf ? 2.0L : 1.0L) / c);
+        host_mid[2 * j] = inv;
+        host_mid[2 * j + 1] = (double) -logl((long double) inv);
+    }
     if (cudaMemcpyToSymbol(g_log_adj, host_log, sizeof host_log) != cudaSuccess ||
-        cudaMemcpyToSymbol(g_exp2_big, host_tab, sizeof host_tab) != cudaSuccess) {
+        cudaMemcpyToSymbol(g_log_mid, host_mid, sizeof host_mid) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_exp2_big, host_tab, sizeof host_tab) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_exp2_rep, host_rep, sizeof host_rep) != cudaSuccess) {
         set_error("upload of the exp table failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
@@ -933,7 +1202,7 @@ int launch_one(Engine& e, const PointwiseArgs& proto, cudaStream_t s) {
     bool& configured = configured_dev[e.device & 63];
     int& occ = occ_dev[e.device & 63];
     // theta staging area sized for a full pass (32 * NPL nodes) so the occupancy is B-independent
-    const size_t kPwSmem = pw_smem_bytes<M>(e.theta_len, 32 * NPL);
+    const size_t kPwSmem = pw_smem_bytes<M, NPL>(e.theta_len, 32 * NPL);
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kPwSmem);
         if (err == cudaSuccess)
@@ -1046,6 +1315,7 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     a.K = e.K;
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
+    for (int j = 0; j < 8; ++j) a.xmax[j] = e.xmax[j];
     if (a.row_end <= a.row_begin) {  // no rows here: zeros (+ the same exchanges the other ranks' launches make)
         if (e.desc.model == PF_MODEL_MIXTURE && !e.f32 && B > 32 && e.gather_per == 0) {
             const int r1 = launch_exchange_only(e, 32, d_out, s, 0, B);
@@ -1199,7 +1469,7 @@ extern "C" PF_API int pf_debug_math(int which, const double* in, double* out, si
     double *d_in = nullptr, *d_out = nullptr;
     if (cudaMalloc(&d_in, n * 8) != cudaSuccess || cudaMalloc(&d_out, n * 8) != cudaSuccess) return PF_ERR_NOMEM;
     cudaMemcpy(d_in, in, n * 8, cudaMemcpyHostToDevice);
-    if (which == 5 || which == 6) {
+    if (which >= 5 && which <= 9) {
         pf::Engine tmp;
         tmp.device = device;
         if (pf::ensure_exp_table_for(tmp) != 0) return PF_ERR_CUDA;

@@ -285,7 +285,9 @@ PF_API const char* pf_last_error(void);                 /* thread-local text of 
 PF_API uint64_t pf_engine_launch_count(const pf_engine* e); /* kernels launched by this engine so far */
 PF_API int pf_device_sm_count(int device);
 /* Diagnostics: apply the engine's device exp(-x/2) (which = 0: double, 2: float; 5: the mixture loop's
- * 2048-entry version) or log(x) (1: double, 3: float, 4: table version, 6: the mixture loop's) elementwise to a HOST array, for accuracy tests of the math kernels. */
+ * 2048-entry degree-3 version; 9: its degree-2 successor, the clamped loop's) or log(x) (1: double, 3: float, 4: table
+ * version, 6: the mixture loop's degree-6 version, 8: the degree-4 version with the exponent accumulated apart), or
+ * 2^x (7: the factored mixture loop's) elementwise to a HOST array, for accuracy tests of the math kernels. */
 PF_API int pf_debug_math(int which, const double* in, double* out, size_t n, int device);
 /* Diagnostics: measured FP64 FMA throughput (1e12 FMA/s) for warps/SM in {4,8,16,32} x
  * independent chains per thread in {1,2,4,8}; out16[4*w + i].  The largest entry is the FP64

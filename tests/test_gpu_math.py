@@ -98,3 +98,45 @@ def test_mixture_loop_log_fp64():
     err = np.abs(got - want)
     assert np.max(err / np.maximum(np.abs(want), 1.0)) < 6e-16  # absolute next to 1, relative elsewhere
     assert got[300000 + 100000 + 50000] == 0.0                  # log(1) exact
+
+
+def test_mixture_loop_exp2_fp64():
+    """mix_exp_accumulate_z (the factored loop): 2^z by the 256-entry table (16 conflict-free copies in shared memory)
+    and the degree-3 minimax polynomial on |g| <= 2^-9: truncation <= 1.8e-14 relative."""
+    rng = np.random.RandomState(7)
+    z = np.concatenate([rng.uniform(-60, 60, 400000), rng.uniform(-512, 512, 100000), [0.0, 1.0, -1.0, 511.9, -511.9]])
+    got = run(7, z)
+    want = np.exp2(z.astype(np.longdouble)).astype(np.float64)
+    rel = (got - want) / want
+    assert np.abs(rel).max() < 2e-14
+    assert abs(rel[:400000].mean()) < 2e-15          # no bias to speak of: what a SUM over rows sees
+    assert got[400000 + 100000] == pytest.approx(1.0, rel=2e-14)
+
+
+def test_mixture_loop_exp_clamped_fp64():
+    """mix_exp_accumulate_e (the clamped squared-distance loop): same polynomial and table, clamp at e = 1408."""
+    rng = np.random.RandomState(8)
+    e = np.concatenate([rng.uniform(0, 60, 300000), rng.uniform(0, 1400, 100000), 10.0 ** rng.uniform(-12, 1, 50000),
+                        [0.0, 1e-300, 1407.9, 1408.0, 1500.0, 1e6, 1e12, 1e300, np.inf]])
+    got = run(9, e)
+    want = np.exp(-0.5 * e.astype(np.longdouble)).astype(np.float64)
+    ok = e < 1400
+    rel = np.abs(got[ok] - want[ok]) / want[ok]
+    assert rel.max() < 7e-14                     # 1.8e-14 truncation + |z| 2^-53 argument rounding near the edge
+    assert rel[e[ok] < 60].max() < 2.5e-14
+    assert np.all(got[~ok] < 2.0 ** -1000) and np.all(got[~ok] >= 0.0)  # clamped: tiny, finite, never wrapped
+    assert np.all(np.isnan(run(9, np.array([np.nan]))) | (run(9, np.array([np.nan])) < 2.0 ** -1000))
+
+
+def test_mixture_loop_log_degree4_fp64():
+    """log_pos_acc + log_n_times_ln2: degree-4 series on |r| <= 2^-9 (r^5/5 <= 5.7e-15 absolute) with n ln 2 added
+    apart -- the form the kernels use, where n is summed as an integer over a lane's rows of a tile."""
+    rng = np.random.RandomState(9)
+    x = np.concatenate([rng.uniform(1e-3, 8.0, 300000), 10.0 ** rng.uniform(-280, 300, 100000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 50000), [1.0, 2.0, 0.5, np.sqrt(2), 1 / np.sqrt(2),
+                                                                 1.4140625, 1.41406249, 0.70703125]])
+    got = run(8, x)
+    want = np.log(x.astype(np.longdouble)).astype(np.float64)
+    err = np.abs(got - want)
+    assert np.max(err / np.maximum(np.abs(want), 1.0)) < 7e-15
+    assert abs(got[300000 + 100000 + 50000]) < 7e-15            # log(1): not exact with midpoint tables, and need not be

@@ -224,6 +224,43 @@ def test_mixture_edge_cases(fb, orc):
 
 
 # ------------------------------------------------------------------------------------ lasso
+def test_mixture_factored_and_clamped_forms_agree_with_the_oracle(fb, orc):
+    """The FP64 mixture kernel scores a frontier with the factored exponent z_k = A_k + B_k.x when every node's theta
+    passes the range test against the data's bounding box (|A_k| + sum_j |B_kj| max|x_j| <= 512) and with the clamped
+    squared-distance form otherwise; the switch is per call, for the whole frontier.  Both sides of it, the frontier
+    that straddles it, and thetas at the edge of the range, against the oracle."""
+    from fetching_b200 import models
+    data, pos = models.mixture_dataset(40000, 8, 2, seed=11)
+    near = models.mixture_thetas(pos, 6, seed=1)                      # |theta| <= ~2.2: factored
+    far = near.copy()
+    far[:, 0:2] += 40.0                                               # one component 40 away: |A_k| ~ 2300, clamped form
+    edge = near.copy()
+    edge[:, 2:4] = [12.0, -12.0]                                      # |A_k| = 208, bound ~ 430: still factored
+    over = near.copy()
+    over[:, 2:4] = [15.0, -15.0]                                      # |A_k| = 325, bound ~ 560: clamped
+    with fb.FrontierEngine.mixture(data, 8, 1000) as e:
+        for name, th in (("near", near), ("far", far), ("edge", edge), ("over", over),
+                         ("mixed", np.concatenate([near[:3], far[:2], edge[:1]]))):
+            s, q = e.eval_frontier(th)
+            want = orc.mixture_frontier(data, th, 1000)
+            assert rel(s, want[0]) < 1e-12 and rel(q, want[1]) < 1e-12, name
+        # the same node scored inside a frontier that passes the test and inside one that does not: two code paths,
+        # one number up to rounding
+        s_f, _ = e.eval_frontier(near)
+        s_c, _ = e.eval_frontier(np.concatenate([near, far[:1]]))
+        assert rel(s_c[:6], s_f) < 1e-13
+    # d = 8, K = 8 (the reference model's own shape) through both forms
+    data8, pos8 = models.mixture_dataset(20000, 8, 8, seed=12)
+    th8 = models.mixture_thetas(pos8, 5, seed=2)
+    far8 = th8.copy()
+    far8[:, :8] += 12.0                                               # |theta_0|^2 ~ 1150: clamped form
+    with fb.FrontierEngine.mixture(data8, 8, 500) as e:
+        for th in (th8, far8):
+            s, q = e.eval_frontier(th)
+            want = orc.mixture_frontier(data8, th, 500)
+            assert rel(s, want[0]) < 1e-12 and rel(q, want[1]) < 1e-12
+
+
 def test_blasso_vs_reference_python_golden(fb, py_models):
     """Golden values are outputs of the reference's own BLasso.evaluate (18000-row items)."""
     g = py_models
