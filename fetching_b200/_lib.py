@@ -103,6 +103,7 @@ SYMBOLS = {
     "pf_debug_dmma_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_issue_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_rf_probe": (C.c_int, [C.c_int, _dp]),
+    "pf_debug_launch_probe": (C.c_int, [C.c_int, _dp]),
 }
 
 _lib = None

@@ -312,3 +312,82 @@ extern "C" PF_API int pf_debug_rf_probe(int device, double* out3) {
     cudaFree(d_out);
     return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer call floor: one kernel launch whose last thread delivers a self-validating word to mapped pinned
+// memory, polled by the host -- the skeleton of pf_eval_frontier without any scoring.  Measured for a small and a
+// 3.6 KB parameter block (PointwiseArgs carries up to 432 inline doubles) and for 1 CTA vs a full grid of
+// 2 x 148 x 256 threads with a ticket (what the frontier kernels do).  out[4] = microseconds per call:
+// {small params, 1 CTA}, {3.6 KB params, 1 CTA}, {small, full grid + ticket}, {3.6 KB, full grid + ticket}.
+// ---------------------------------------------------------------------------------------------------------------
+namespace pf {
+struct ProbeSmall {
+    unsigned long long* out;
+    unsigned int* ticket;
+    unsigned long long seq;
+};
+struct ProbeBig {
+    unsigned long long* out;
+    unsigned int* ticket;
+    unsigned long long seq;
+    double pad[448];
+};
+template <class A>
+__global__ void __launch_bounds__(256) launch_probe_kernel(const __grid_constant__ A a) {
+    __shared__ int last;
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(a.ticket, 1u);
+        last = prev == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *a.ticket = 0u;
+        *reinterpret_cast<volatile unsigned long long*>(a.out) = a.seq;
+    }
+}
+template <class A>
+static double launch_probe_run(unsigned grid, int iters, unsigned long long* h_out, unsigned long long* d_out,
+                               unsigned int* d_ticket, cudaStream_t s, unsigned long long& seq) {
+    A a{};
+    a.out = d_out;
+    a.ticket = d_ticket;
+    auto once = [&]() {
+        a.seq = ++seq;
+        launch_probe_kernel<A><<<grid, 256, 0, s>>>(a);
+        volatile unsigned long long* w = h_out;
+        while (*w != a.seq) __builtin_ia32_pause();
+    };
+    for (int i = 0; i < 20; ++i) once();
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < iters; ++i) once();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return ((double) (t1.tv_sec - t0.tv_sec) * 1e6 + 1e-3 * (double) (t1.tv_nsec - t0.tv_nsec)) / iters;
+}
+}  // namespace pf
+
+extern "C" PF_API int pf_debug_launch_probe(int device, double* out4) {
+    if (!out4 || cudaSetDevice(device) != cudaSuccess) return PF_ERR_INVALID;
+    cudaStream_t s;
+    unsigned long long *h_out = nullptr, *d_out = nullptr;
+    unsigned int* d_ticket = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(&h_out, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&d_out, h_out, 0) != cudaSuccess || cudaMalloc(&d_ticket, 64) != cudaSuccess ||
+        cudaMemset(d_ticket, 0, 64) != cudaSuccess)
+        return PF_ERR_CUDA;
+    *h_out = 0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const unsigned full = 2u * (unsigned) prop.multiProcessorCount;
+    unsigned long long seq = 0;
+    out4[0] = pf::launch_probe_run<pf::ProbeSmall>(1, 2000, h_out, d_out, d_ticket, s, seq);
+    out4[1] = pf::launch_probe_run<pf::ProbeBig>(1, 2000, h_out, d_out, d_ticket, s, seq);
+    out4[2] = pf::launch_probe_run<pf::ProbeSmall>(full, 2000, h_out, d_out, d_ticket, s, seq);
+    out4[3] = pf::launch_probe_run<pf::ProbeBig>(full, 2000, h_out, d_out, d_ticket, s, seq);
+    cudaStreamSynchronize(s);
+    cudaFree(d_ticket);
+    cudaFreeHost(h_out);
+    cudaStreamDestroy(s);
+    return PF_OK;
+}

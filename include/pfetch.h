@@ -302,6 +302,11 @@ PF_API int pf_debug_issue_probe(int device, double* out4);
  * 2-register DFMA with 2 and 4 one-register ALU instructions between (register-file bandwidth); 5 values. */
 PF_API int pf_debug_rf_probe(int device, double* out5);
 
+/* Diagnostics: the floor of a host-buffer call -- microseconds per {kernel launch, one word delivered to mapped host
+ * memory, host polls it} for {24-byte parameters, 1 CTA}, {3.6 KB parameters, 1 CTA}, {24 B, 2 x SMs CTAs + ticket},
+ * {3.6 KB, 2 x SMs CTAs + ticket}: what pf_eval_frontier costs before any scoring. */
+PF_API int pf_debug_launch_probe(int device, double* out4);
+
 #ifdef __cplusplus
 }
 #endif

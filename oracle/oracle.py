@@ -26,6 +26,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "pf_ref")
+REF_GPU_BIN = os.path.join(HERE, "_ref", "pf_ref_gpu")
 
 _dp = C.POINTER(C.c_double)
 _ldp = C.POINTER(C.c_longdouble)
@@ -39,6 +40,13 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-s", "-C", HERE, "port"], check=True)
     if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_BIN)):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+    # the reference tree + the product's C ABI in one binary (needs the built libpfetch.so; runs on a GPU box only)
+    pflib = os.path.join(os.path.dirname(HERE), "fetching_b200", "lib", "libpfetch.so")
+    srcs = [os.path.join(HERE, f) for f in ("ref_gpu_driver.cc", "ref_driver.cc")] + [pflib]
+    if os.path.isdir("/root/reference") and os.path.exists(pflib) and (
+            force or not os.path.exists(REF_GPU_BIN) or
+            os.path.getmtime(REF_GPU_BIN) < max(os.path.getmtime(x) for x in srcs)):
+        subprocess.run(["make", "-s", "-C", HERE, "ref-gpu"], check=True)
 
 
 def lib() -> C.CDLL:

@@ -343,6 +343,7 @@ int cmd_normal_bench(size_t n, size_t nodes, size_t reps, size_t threads) {
 
 } // namespace
 
+#ifndef PF_REF_DRIVER_NO_MAIN  /* ref_gpu_driver.cc includes this file for its helpers and brings its own main() */
 int main(int argc, char** argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: pf_ref unit | chain [normal|boltzmann] [-n C] [-d N] [-b B] [-l L] [-s P] "
@@ -376,3 +377,4 @@ int main(int argc, char** argv) {
     }
     return 1;
 }
+#endif
