@@ -421,6 +421,34 @@ def numpy_one_core(kind, prm, budget_s=3.0):
                       (done, ir, per_item * 1e6, n_items_total)}
 
 
+def reference_mpirun_chain(levels=300):
+    """BASELINE.md section 3, baseline 1(b), for C1: the reference's own parallel program -- JobTree::run_master on rank
+    0, the registered normal sampler's work() -> worker<NormalSampler<2>>() on ranks 1..np-1, N = 10^6 points per
+    worker (samplers/normal.cc) -- compiled in place from the reference sources with THREADS for ranks
+    (`oracle/_ref/pf_ref mpirun`, thread-mailbox boost::mpi shim), np = all host threads.  Chain steps/s from the
+    time stamps of the TSV it prints (first to last level, data-set construction excluded) and the stock
+    `OK sample/s` figure (everything included).  None when the binary did not travel."""
+    from oracle import oracle as orc
+    if not orc.have_pf_ref():
+        return None
+    np_ranks = max(2, host_cores())
+    try:
+        p = subprocess.run([orc.REF_BIN, "mpirun", "-np", str(np_ranks), "normal", "-l", str(levels)],
+                           capture_output=True, text=True, timeout=600)
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    rows = [l.split("\t") for l in p.stdout.splitlines() if l[:1].isdigit()]
+    ok = [l for l in p.stderr.splitlines() if l.startswith("OK sample/s")]
+    if p.returncode != 0 or len(rows) < 3 or not ok:
+        return None
+    t0, t1 = float(rows[1][0]), float(rows[-1][0])
+    return {"steps_per_sec": (int(rows[-1][1]) - int(rows[1][1])) / max(t1 - t0, 1e-9), "np": np_ranks,
+            "levels": int(rows[-1][1]), "ok_line_samples_per_sec": float(ok[0].split("=")[1].split()[0]),
+            "accept_rate": sum(int(r[2]) for r in rows[1:]) / max(1, len(rows) - 1),
+            "kind": "reference source (master.cc, masterloop.cc, worker.hh, samplers/normal.cc) rebuilt against a shim, "
+                    "threads for MPI ranks; not the stock Boost.MPI binary"}
+
+
 # ------------------------------------------------------------------------------------------ GPU helpers
 class Ctx:
     """torch / torch.distributed handles + this process's place in the job."""
@@ -525,7 +553,9 @@ def time_engine(ctx, eng, thetas, B, K, W):
     for _ in range(W):
         eng.eval_frontier(thetas)
     ctx.barrier()
-    s_host, q_host, t_e2e = eng.eval_frontier_repeat(thetas, K)
+    # the step's inputs start in PINNED host memory (the engine's staging buffer: what a master that assembles the
+    # burst's proposals into one buffer hands over) and travel to the device inside the timed call
+    s_host, q_host, t_e2e = eng.eval_frontier_repeat(thetas, K, pinned=True)
     torch.cuda.synchronize()
     return dict(ms_total=ms_total, launches=int(launches), dev=dev, host_s=s_host, host_q=q_host,
                 e2e_s=ctx.max_over_ranks(t_e2e))
@@ -592,6 +622,10 @@ def small_config(ctx, name, B, dtype, K, W, chain_levels):
     if chain_levels:
         out["chain"] = chain_run(ctx, eng, chain_kwargs(kind, prm, shard, B, chain_levels))
     eng.close()
+    if name == "normal1e6":
+        ref = reference_mpirun_chain()
+        if ref:
+            out["reference_cpu_chain"] = ref
     return out
 
 

@@ -95,30 +95,42 @@ struct FrontierEvaluator {
     std::size_t shards = 1;
     bool failed() const { return status != PF_OK; }
     std::vector<double> thetas;
+    // where the frontier is assembled: the engine's pinned staging buffer when it fits (DMA'd in place by the eval
+    // calls, pf_engine_theta_buffer), else a vector of this evaluator's own
+    double* staging(std::size_t nodes) {
+        const std::size_t need = nodes * (std::size_t) theta_len;
+        if (engine) {
+            uint64_t cap = 0;
+            double* pinned = pf_engine_theta_buffer(engine, &cap);
+            if (pinned && need <= cap) return pinned;
+        }
+        thetas.assign(need, 0.0);
+        return thetas.data();
+    }
     void operator()(const std::vector<FrontierJob>& jobs, std::vector<double>& sum, std::vector<double>& sum_sq) {
-        thetas.assign(jobs.size() * (std::size_t) theta_len, 0.0);
+        double* th = staging(jobs.size());
         for (std::size_t i = 0; i < jobs.size(); ++i)
-            load_doubles(jobs[i].theta, &thetas[i * theta_len], theta_len);
-        const int r = engine ? pf_eval_frontier(engine, (uint32_t) jobs.size(), thetas.data(), sum.data(), sum_sq.data())
-                             : fn(user, (uint32_t) jobs.size(), thetas.data(), sum.data(), sum_sq.data());
+            load_doubles(jobs[i].theta, &th[i * theta_len], theta_len);
+        const int r = engine ? pf_eval_frontier(engine, (uint32_t) jobs.size(), th, sum.data(), sum_sq.data())
+                             : fn(user, (uint32_t) jobs.size(), th, sum.data(), sum_sq.data());
         if (r != PF_OK && status == PF_OK) status = r;
     }
     // items [first, first + count) of every node; the normal target walks them in each node's own order
     void range(const std::vector<FrontierJob>& jobs, std::size_t first, std::size_t count, std::vector<double>& sum,
                std::vector<double>& sum_sq) {
-        thetas.assign(jobs.size() * (std::size_t) theta_len, 0.0);
+        double* th = staging(jobs.size());
         order.assign(jobs.size() * 2, 0);
         for (std::size_t i = 0; i < jobs.size(); ++i) {
-            load_doubles(jobs[i].theta, &thetas[i * theta_len], theta_len);
+            load_doubles(jobs[i].theta, &th[i * theta_len], theta_len);
             order[2 * i] = jobs[i].order_stride;
             order[2 * i + 1] = jobs[i].order_start;
         }
         int r;
         if (engine)
-            r = pf_eval_frontier_range(engine, (uint32_t) jobs.size(), thetas.data(), first / shards, count / shards,
+            r = pf_eval_frontier_range(engine, (uint32_t) jobs.size(), th, first / shards, count / shards,
                                        ordered ? order.data() : nullptr, sum.data(), sum_sq.data());
         else
-            r = range_fn ? range_fn(user, (uint32_t) jobs.size(), thetas.data(), first, count, order.data(), sum.data(),
+            r = range_fn ? range_fn(user, (uint32_t) jobs.size(), th, first, count, order.data(), sum.data(),
                                     sum_sq.data())
                          : PF_ERR_UNSUPPORTED;
         if (r != PF_OK && status == PF_OK) status = r;

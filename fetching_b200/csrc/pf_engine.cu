@@ -502,8 +502,12 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
         // one kernel, results + completion flag in mapped host memory
         if (e.desc.model == PF_MODEL_NORMAL) e.normal_general = !all_identity_cov(e, thetas + (size_t) lo * e.theta_len, nloc);
         const size_t tbytes = (size_t) nloc * e.theta_len * 8;
-        memcpy(e.h_theta, thetas + (size_t) lo * e.theta_len, tbytes);
-        PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
+        const double* src = thetas + (size_t) lo * e.theta_len;
+        if (!(src >= e.h_theta && src + (size_t) nloc * e.theta_len <= e.h_theta + (size_t) e.max_frontier * e.theta_len)) {
+            memcpy(e.h_theta, src, tbytes);
+            src = e.h_theta;
+        }
+        PF_CUDA(cudaMemcpyAsync(e.d_theta, src, tbytes, cudaMemcpyHostToDevice, e.stream));
         e.done_seq = next_host_seq(e);
         e.done_flag = reinterpret_cast<unsigned long long*>(e.d_hout);
         e.gather_per = per;
@@ -592,8 +596,15 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         const bool inline_theta = fast && e.allow_inline_theta && (e.desc.model == PF_MODEL_NORMAL || e.desc.model == PF_MODEL_MIXTURE) &&
                                   (size_t) nb * e.theta_len <= (size_t) kInlineThetaDoubles;
         if (!inline_theta) {
-            memcpy(e.h_theta, th, tbytes);
-            PF_CUDA(cudaMemcpyAsync(e.d_theta, e.h_theta, tbytes, cudaMemcpyHostToDevice, e.stream));
+            // through the engine's pinned staging buffer -- unless the caller already wrote the frontier there
+            // (pf_engine_theta_buffer): then the DMA reads it in place and the host-side copy (25-40 us for the 512 KB of
+            // a dense Boltzmann frontier) is saved
+            const double* src = th;
+            if (!(th >= e.h_theta && th + (size_t) nb * e.theta_len <= e.h_theta + (size_t) e.max_frontier * e.theta_len)) {
+                memcpy(e.h_theta, th, tbytes);
+                src = e.h_theta;
+            }
+            PF_CUDA(cudaMemcpyAsync(e.d_theta, src, tbytes, cudaMemcpyHostToDevice, e.stream));
         }
         int r;
         if (fast) {
@@ -706,6 +717,13 @@ int pf_engine_group(const pf_engine* pe, int* rank, int* nranks, int* node_split
     if (nranks) *nranks = e.nranks;
     if (node_split) *node_split = e.node_split ? 1 : 0;
     return PF_OK;
+}
+
+double* pf_engine_theta_buffer(pf_engine* pe, uint64_t* capacity_doubles) {
+    if (!pe) return nullptr;
+    Engine& e = *reinterpret_cast<Engine*>(pe);
+    if (capacity_doubles) *capacity_doubles = (uint64_t) e.max_frontier * e.theta_len;
+    return e.h_theta;
 }
 
 uint64_t pf_engine_launch_count(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->launches : 0; }

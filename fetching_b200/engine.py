@@ -100,10 +100,22 @@ class FrontierEngine:
                                          q.ctypes.data_as(_dp)), "pf_eval_frontier")
         return s, q
 
-    def eval_frontier_repeat(self, thetas, iters: int):
-        """`iters` complete host-buffer calls in a C loop; returns (sum, sum_sq, seconds)."""
+    def theta_buffer(self) -> np.ndarray:
+        """The engine's pinned staging buffer as a [max_frontier][theta_len] array (pf_engine_theta_buffer): a frontier
+        written here and passed to the eval calls is DMA'd in place, without the engine's own staging copy."""
+        cap = C.c_uint64(0)
+        p = self._lib.pf_engine_theta_buffer(self._h, C.byref(cap))
+        return np.ctypeslib.as_array(p, shape=(int(cap.value) // self.theta_len, self.theta_len))
+
+    def eval_frontier_repeat(self, thetas, iters: int, pinned: bool = False):
+        """`iters` complete host-buffer calls in a C loop; returns (sum, sum_sq, seconds).  pinned = True: the frontier
+        is first placed in the engine's pinned staging buffer (outside the timed loop) and read from there."""
         t = self._thetas(thetas)
         B = t.shape[0]
+        if pinned and B <= self.max_frontier:
+            buf = self.theta_buffer()
+            buf[:B] = t
+            t = buf[:B]
         s, q = np.empty(B), np.empty(B)
         sec = C.c_double(0.0)
         check(self._lib.pf_eval_frontier_repeat(self._h, B, t.ctypes.data_as(_dp), s.ctypes.data_as(_dp),

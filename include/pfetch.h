@@ -131,6 +131,13 @@ PF_API int pf_engine_group(const pf_engine* e, int* rank, int* nranks, int* node
  * in `sum` / `sum_sq`. */
 PF_API int pf_eval_frontier(pf_engine* e, uint32_t B, const double* thetas, double* sum, double* sum_sq);
 
+/* Optional zero-copy staging: a PINNED host buffer owned by the engine, room for pf_engine_max_frontier() nodes
+ * (*capacity_doubles, if non-NULL).  A caller that assembles its frontier there ([B][theta_len], from the start of the
+ * buffer) and passes that pointer as `thetas` to pf_eval_frontier / _range / _repeat saves the engine's own copy into
+ * pinned memory in front of the host->device DMA -- what a master that gathers the nodes' proposals (protocol.hh:200-206
+ * strings) into one buffer anyway should do.  Any other pointer works as before.  Valid until pf_engine_destroy. */
+PF_API double* pf_engine_theta_buffer(pf_engine* e, uint64_t* capacity_doubles);
+
 /* The same call `iters` times back to back (every iteration a complete pf_eval_frontier: theta from the host
  * buffer, kernel, results back in `sum` / `sum_sq`), timed with the host's monotonic clock into *seconds.  What a
  * C++ master's loop costs per burst, without a scripting language's per-call overhead in between (bench.py). */

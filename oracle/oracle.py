@@ -174,6 +174,22 @@ def boltzmann_dense_logp(W, x, temperature=1.0):
     return float(lib().orc_boltzmann_dense_logp(_p(W), W.shape[0], _p(x), temperature))
 
 
+def boltzmann_dense_logp_independent(W, x, temperature=1.0):
+    """A SECOND, unrelated statement of the dense Boltzmann energy -x'Wx/T, for a model that has no reference
+    implementation to pin against (boltzmannsampler.hh:71-74 is a scalar toy): instead of the row-by-row double loop of
+    loglik_oracle.c it sums the symmetric half
+        sum_i W_ii x_i^2 + sum_{i<j} (W_ij + W_ji) x_i x_j
+    in 80-bit extended precision with numpy's pairwise summation.  Different formula path, different summation order,
+    different precision: agreement of the C restatement, the CUDA-core kernel and the DMMA kernel with THIS is the
+    strongest check the workload admits (it remains "parity unpinned" with respect to the reference)."""
+    W = np.asarray(W, dtype=np.longdouble)
+    x = np.asarray(x, dtype=np.longdouble)
+    iu = np.triu_indices(W.shape[0], k=1)
+    diag = np.sum(np.diagonal(W) * x * x)
+    off = np.sum((W[iu] + W.T[iu]) * (x[iu[0]] * x[iu[1]]))
+    return -(diag + off) / np.longdouble(temperature)
+
+
 def boltzmann_dense_eval_ld(W, x, temperature=1.0):
     W, x = _c(W), _c(x)
     s, q = C.c_longdouble(0), C.c_longdouble(0)

@@ -17,6 +17,9 @@
  *   normal-bench N B REPS        times evaluate_many for B nodes (CPU baseline, kind
  *                                "reference", one thread per node like one MPI worker per node)
  *   data N                       prints the first values of the normal.cc:41-46 dataset
+ *   mpirun -np N SAMPLER ...     the reference's parallel program, threads for ranks: run_master(world) on rank 0,
+ *                                the registered sampler's work() -> worker<>() on ranks 1..N-1, over the
+ *                                thread-mailbox boost::mpi::communicator of oracle/shim (the CPU baseline of C1)
  *   frontier SAMPLER ...         the reference JobTree + run_master driven by the product's
  *                                FrontierCommunicator (whole scheduling bursts scored at once by the
  *                                reference's own evaluate_many): prints every JobInfo handed out
@@ -343,6 +346,77 @@ int cmd_normal_bench(size_t n, size_t nodes, size_t reps, size_t threads) {
 
 } // namespace
 
+/* `pf_ref mpirun -np N [-S] SAMPLER [-l L] [-b B] [-y STYLE] [-s POLICY] [-r RATIO] [-c CORR] [-d DIM] [-t]`
+ * The reference's parallel program with THREADS for ranks: rank 0 builds the JobTree and runs
+ * JobTree::run_master(world, ...) (tree.cc:144-152, master.cc:551-556, masterloop.cc), ranks 1..N-1 run the registered
+ * sampler's work() (samplers/normal.cc:38-49 -> worker<NormalSampler<2>>(), worker.hh:53-177), all unmodified and
+ * compiled in place; only boost::mpi::communicator is the thread-mailbox shim (oracle/shim/boost/mpi/communicator.hpp).
+ * stdout: the stock TSV of stype.cc:67-84; stderr: the stock `OK sample/s` line (tree.cc:160-167). */
+int cmd_mpirun(int argc, char** argv) {
+    const char* sampler_name = 0;
+    int np = 2, chain_length = 100, batch_size = 1000, dimension = 1, update_style = INCREMENTAL,
+        scheduling_policy = PREDICTIVE;
+    double reassign_ratio = 1.1, correlation = 0.99;
+    bool threshold = false;
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
+        if (a == "-np") np = atoi(next());
+        else if (a == "-S") sampler_name = next();
+        else if (a == "-l") chain_length = atoi(next());
+        else if (a == "-b") batch_size = atoi(next());
+        else if (a == "-y") update_style = atoi(next());
+        else if (a == "-s") scheduling_policy = atoi(next());
+        else if (a == "-r") reassign_ratio = strtod(next(), 0);
+        else if (a == "-c") correlation = strtod(next(), 0);
+        else if (a == "-d") dimension = atoi(next());
+        else if (a == "-t") threshold = true;
+        else sampler_name = argv[i];
+    }
+    if (!sampler_name) sampler_name = "normal";
+    if (np < 2) {
+        fprintf(stderr, "mpirun: -np must be at least 2 (one master, one worker)\n");
+        return 2;
+    }
+    SamplerType* sampler = SamplerType::find(sampler_name);
+    if (!sampler) {
+        std::cerr << "No such sampler \"" << sampler_name << "\"\n";
+        SamplerType::print_list();
+        return 1;
+    }
+    const double tic = timestamp();
+    boost::mpi::shim::World threads_as_ranks(np);
+    boost::mpi::shim::world() = &threads_as_ranks;
+    boost::mpi::communicator world;
+    std::vector<std::thread> ranks;
+    for (int r = 1; r < np; ++r)
+        ranks.emplace_back([&, r]() {
+            boost::mpi::shim::my_rank() = r;
+            world.barrier();
+            sampler->work(world, (size_t) batch_size, (size_t) update_style, 0);  // tree.cc:153-154
+        });
+    boost::mpi::shim::my_rank() = 0;
+    world.barrier();
+    fprintf(stderr, "# pf_ref mpirun -np %d (threads for ranks) -S %s -l %d -b %d -d %d -r %g -c %g%s -y %d -s %d\n", np,
+            sampler_name, chain_length, batch_size, dimension, reassign_ratio, correlation, threshold ? " -t" : "",
+            update_style, scheduling_policy);
+    {
+        JobTree master_tree(np, chain_length, sampler, scheduling_policy, correlation, dimension);  // tree.cc:147-152
+        master_tree.set_reassign_ratio(reassign_ratio);
+        master_tree.set_require_comparison_theta(false);
+        master_tree.set_threshold(threshold);
+        sampler->notify(master_tree, 0, 0, std::string(), false);
+        master_tree.run_master(world, JobTree::run_behavior().quiet(true));
+    }
+    for (auto& t : ranks) t.join();
+    const double toc = timestamp();
+    fflush(stdout);
+    fprintf(stderr, "OK sample/s = %-7.3f samples = %-6d seconds = %-7.3f N = %d\n", chain_length / (toc - tic),
+            chain_length, toc - tic, np);
+    boost::mpi::shim::world() = nullptr;
+    return 0;
+}
+
 #ifndef PF_REF_DRIVER_NO_MAIN  /* ref_gpu_driver.cc includes this file for its helpers and brings its own main() */
 int main(int argc, char** argv) {
     if (argc < 2) {
@@ -369,6 +443,8 @@ int main(int argc, char** argv) {
                                 strtoull(argv[4], 0, 0), argc > 5 ? strtoull(argv[5], 0, 0) : 0);
     else if (cmd == "frontier")
         return cmd_frontier(argc - 2, argv + 2);
+    else if (cmd == "mpirun")
+        return cmd_mpirun(argc - 2, argv + 2);
     else if (cmd == "data" && argc == 3) {
         size_t n = strtoull(argv[2], 0, 0);
         double* d = normal_dataset(n);

@@ -82,6 +82,16 @@ def test_gpu_normal_chain_c1_full_size(fb, orc):
         s, _ = orc.normal_eval(data, a.theta[i])
         assert abs(a.metric_sum[i] - s) <= 1e-10 * abs(s)
     assert a.stats["levels"] >= 100 and b.stats["engine_calls"] < a.stats["engine_calls"]
+    # ... and the reference's own parallel program at this size (samplers/normal.cc: N = 10^6), threads for MPI ranks
+    if orc.have_pf_ref():
+        out = orc.run_pf_ref("mpirun", "-np", 9, "normal", "-l", 100)
+        rows = [l.split("\t") for l in out.splitlines() if l[:1].isdigit()]
+        assert len(rows) >= 101
+        for i, r in enumerate(rows[:101]):
+            assert (int(r[1]), int(r[2])) == (a.depth[i], a.accept[i]), i
+            assert abs(float(r[3]) - a.metric_sum[i]) <= 1e-10 * abs(a.metric_sum[i]), i
+            want = [float(x) for x in r[4].strip("[]").replace(";", ",").split(",")]
+            assert np.allclose(a.theta[i], want, rtol=6e-6, atol=1e-12), i   # printed with 6 significant digits
 
 
 def test_gpu_normal_chain_d100000_golden(fb, orc):

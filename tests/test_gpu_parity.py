@@ -351,6 +351,9 @@ def test_boltzmann_dense(fb, orc, D, B):
     scale = np.array([np.abs(np.outer(x, x) * W).sum() / 2.0 for x in X])
     assert np.max(np.abs(s - want[0]) / scale) < TOL64
     assert np.max(np.abs(q - s * s) / np.maximum(s * s, 1e-300)) < 1e-14
+    # ... and against the independent statement (symmetric half, pairwise, 80-bit): two unrelated checkers
+    ind = np.array([float(orc.boltzmann_dense_logp_independent(W, x, 2.0)) for x in X])
+    assert np.max(np.abs(s - ind) / scale) < TOL64
     if True:  # tensor-core (DMMA) variant above, CUDA-core variant here
         with fb.FrontierEngine.boltzmann_dense(W, temperature=2.0) as e:
             e.set_option(fb.OPT_MATVEC_TENSOR, 0)

@@ -169,3 +169,37 @@ def test_reference_binary_reproduces_goldens(orc, golden_dir, ref_normal):
     data = orc.normal_dataset(int(ref_normal["n"]))
     res = orc.pf_ref_normal_eval(data, ref_normal["thetas"][:3])
     assert np.array_equal(res[:, 0], ref_normal["sum"][:3])
+
+
+def test_reference_parallel_program_with_threads_for_ranks(orc):
+    """`pf_ref mpirun -np N normal`: the reference's run_master on rank 0 and worker<NormalSampler<2>>() on ranks
+    1..N-1 (samplers/normal.cc, N = 10^6 points each), unmodified, over the thread-mailbox boost::mpi shim.  The chain
+    must not depend on the number of ranks or on thread timing (that is the point of prefetching MH), and its first
+    proposals are the ones every golden chain starts with (same replayable stream)."""
+    if not orc.have_pf_ref():
+        pytest.skip("oracle/_ref/pf_ref not built")
+
+    def chain(np_ranks):
+        out = orc.run_pf_ref("mpirun", "-np", np_ranks, "normal", "-l", 25)
+        rows = [l.split("\t") for l in out.splitlines() if l[:1].isdigit()]
+        return [(int(r[1]), int(r[2]), r[4]) for r in rows], [float(r[3]) for r in rows]
+
+    a, sa = chain(2)
+    b, sb = chain(5)
+    assert len(a) >= 26 and a[:26] == b[:26]
+    assert all(abs(x - y) <= 1e-12 * abs(x) for x, y in zip(sa[:26], sb[:26]))
+    assert a[0] == (0, 1, "[0, 0; 1, 0, 1]") and a[1][2] == "[0.157538, -0.10592; 1, 0, 1]"
+
+
+def test_dense_boltzmann_two_unrelated_statements_agree(orc):
+    """No reference code exists for the dense energy, so the C restatement is checked against an independent one:
+    symmetric half, pairwise summation, 80-bit (oracle.boltzmann_dense_logp_independent)."""
+    from fetching_b200 import models
+    for D, seed in ((64, 1), (200, 2), (1024, 3)):
+        W, X = models.boltzmann_dataset(D, 3, seed=seed)
+        W = W + 0.3 * np.random.RandomState(seed).standard_normal((D, D)) / np.sqrt(D)   # not symmetric on purpose
+        for x in X:
+            a = orc.boltzmann_dense_logp(W, x, 1.7)
+            b = orc.boltzmann_dense_logp_independent(W, x, 1.7)
+            scale = np.abs(np.outer(x, x) * W).sum() / 1.7
+            assert abs(a - float(b)) <= 2e-16 * D * scale / np.sqrt(D) + 1e-13 * abs(float(b))
