@@ -348,8 +348,14 @@ static int create(const pf_model_desc* d, Engine** out) {
         }
     } else if (is_matvec(*e)) {
         const uint32_t kch = (uint32_t) (128 / esz);
-        e->cols_pad = (e->dim + kch - 1) / kch * kch;  // row pitch in elements (multiple of one 128-byte chunk)
-        const size_t pitch = (size_t) e->cols_pad * esz;
+        e->cols_pad = (e->dim + kch - 1) / kch * kch;  // columns rounded up to whole 128-byte chunks
+        // Row pitch: whole chunks, but never a multiple of 2 KB.  A box is <= 256 rows x one 128-byte chunk, i.e. that many
+        // requests exactly one pitch apart; with a power-of-two pitch (p = 1000 floats -> 4096 B) they all land on the same
+        // HBM channel and queue up behind each other (ncu: 30 % DRAM throughput, 6 us per box) -- one chunk of padding per
+        // row spreads them over the channels.
+        size_t pitch = (size_t) e->cols_pad * esz;
+        if (pitch % 2048 == 0) pitch += 128;
+        e->pitch_bytes = pitch;
         const size_t bytes = pitch * e->n_rows + 1024;
         PF_CUDA_F(cudaMalloc(&e->d_data, bytes));
         PF_CUDA_F(cudaMemsetAsync(e->d_data, 0, bytes, e->stream));
@@ -373,7 +379,8 @@ static int create(const pf_model_desc* d, Engine** out) {
             PF_CUDA_F(cudaMemcpyAsync(e->d_resp, d->response, e->n_rows * 8, cudaMemcpyHostToDevice, e->stream));
             PF_CUDA_F(cudaStreamSynchronize(e->stream));
         }
-        PF_CUDA_F(cudaMalloc(&e->d_betaT, (size_t) e->cols_pad * kMaxNodesPerPass * esz));
+        // coefficient panel: [cols_pad][64] of T, or hi + lo float parts for the tcgen05 path (both fit 8 bytes per entry)
+        PF_CUDA_F(cudaMalloc(&e->d_betaT, (size_t) e->cols_pad * kMaxNodesPerPass * 8));
     }
 
     // ---- per-call buffers
@@ -734,7 +741,7 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
     switch (option) {
         case PF_OPT_ASSUME_IDENTITY_COV: e.normal_general = value == 0; e.assume_identity = value != 0; return PF_OK;
         case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
-        case PF_OPT_MATVEC_TENSOR: e.mv_tensor = value != 0; return PF_OK;
+        case PF_OPT_MATVEC_TENSOR: e.mv_tensor = value != 0; e.mv_tensor_force = value == 2; return PF_OK;
         case PF_OPT_INLINE_THETA: e.allow_inline_theta = value != 0; return PF_OK;
         case PF_OPT_PEER_EXCHANGE:
             if (value != 0 && !e.peer_attached) {

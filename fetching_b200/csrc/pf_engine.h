@@ -98,11 +98,13 @@ struct Engine {
     uint64_t n_rows = 0, n_items = 0, item_rows = 1;
     uint32_t dim = 0, K = 0, theta_len = 0, max_frontier = 64;
     uint32_t cols_pad = 0;
+    size_t pitch_bytes = 0;      // matrix models: bytes between consecutive rows of the resident matrix (>= cols_pad * esz)
     double temperature = 1.0;
     double xmax[8];              // pointwise models: max |x_j| per column of the resident rows (see PointwiseArgs)
     bool normal_general = true;  // per call: some node has a non-identity covariance (or unknown)
     bool assume_identity = false;  // PF_OPT_ASSUME_IDENTITY_COV
-    bool mv_tensor = true;         // PF_OPT_MATVEC_TENSOR: DMMA variant of the matvec kernel (FP64 only)
+    bool mv_tensor = true;         // PF_OPT_MATVEC_TENSOR: tensor-core contraction (FP64: DMMA; PF_F32 lasso: tcgen05 3xTF32)
+    bool mv_tensor_force = false;  // PF_OPT_MATVEC_TENSOR = 2: the tcgen05 path for every frontier size (default: B > 32)
 
     void* d_data = nullptr;      // data set (T), padded
     double* d_resp = nullptr;    // lasso response (always double)
@@ -163,6 +165,9 @@ int launch_boltzmann_scalar(Engine& e, uint32_t B, const double* d_theta, double
 // a rank of a peer-exchange group with NO rows in the requested range: takes part in the exchange with zeros
 int launch_exchange_only(Engine& e, uint32_t B, double* d_out, cudaStream_t s, unsigned out_off = 0,
                          unsigned out_stride = 0);
+// PF_F32 lasso on tcgen05 (pf_matvec_tc.cu): fills the tile geometry of `a`, launches the panel prep + frontier kernels
+int launch_matvec_tc32(Engine& e, MatvecArgs& a, const double* d_theta, cudaStream_t s);
+int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out);  // cached 2-D tensor map of the matrix (pf_matvec.cu)
 uint32_t pointwise_max_frontier(const Engine& e);
 int ensure_exp_table_for(Engine& e);  // uploads the mixture loop's exp table to e.device (once per device)
 bool pointwise_supported(const Engine& e);

@@ -509,6 +509,8 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+}  // namespace
+
 int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
     for (int i = 0; i < e.n_tmaps; ++i)
         if (e.tmap_rows[i] == tile_rows) {
@@ -522,7 +524,7 @@ int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
     }
     const size_t esz = e.f32 ? 4 : 8;
     const cuuint64_t dims[2] = {(cuuint64_t) e.dim, (cuuint64_t) e.n_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t) e.cols_pad * esz};
+    const cuuint64_t strides[1] = {(cuuint64_t) e.pitch_bytes};
     const cuuint32_t box[2] = {(cuuint32_t) (MV_CHUNK_BYTES / esz), (cuuint32_t) tile_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, e.f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, e.d_data, dims,
@@ -538,6 +540,8 @@ int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out) {
     }
     return 0;
 }
+
+namespace {
 
 template <typename T, int RPL, bool BOLTZ, int NBK = 0, int MB = 4>
 int launch_mv(Engine& e, MatvecArgs& a, cudaStream_t s) {
@@ -665,6 +669,11 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     a.trace = e.d_trace;
     if (a.row_end <= a.row_begin) return launch_exchange_only(e, B, d_out, s);  // no rows here: zeros (+ the exchange)
     a.xchg = e.next_xchg();
+    // PF_F32 lasso: the contraction on the tcgen05 tensor cores, FP32-faithful (3xTF32, pf_matvec_tc.cu).  Measured at C4
+    // (n = 1e5, p = 1000; ms per call, tcgen05 / CUDA cores): B = 8 0.167 / 0.094, 16 0.176 / 0.118, 32 0.197 / 0.184,
+    // 64 0.244 / 0.351 -- the tensor path pays a fixed ~0.15 ms (X_lo pass + panel re-read per 128-row tile) and wins
+    // once the CUDA cores are FMA-bound: it is the default above 32 nodes, and for any B with PF_OPT_MATVEC_TENSOR = 2.
+    if (e.f32 && !boltz && e.mv_tensor && (B > 32 || e.mv_tensor_force)) return launch_matvec_tc32(e, a, d_theta, s);
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
     static bool prep_configured[64] = {};

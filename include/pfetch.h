@@ -276,9 +276,11 @@ enum pf_option {
     /* Row shards: 1 = reduce inside the frontier kernel over peer memory (default once pf_engine_peer_attach
      * succeeded), 0 = ncclAllReduce after the kernel (needs pf_engine_comm_init). */
     PF_OPT_PEER_EXCHANGE = 3,
-    /* Lasso / dense Boltzmann, FP64: 1 (default) = contraction on the FP64 tensor cores (mma.sync.m8n8k4.f64,
-     * DMMA), 0 = FP64 FMA on the CUDA cores (the variant PF_F32 always uses).  Same IEEE arithmetic,
-     * different summation order over the columns. */
+    /* Lasso / dense Boltzmann: 1 (default) = contraction on the tensor cores, 0 = FMA on the CUDA cores.
+     * FP64: mma.sync.m8n8k4.f64 (DMMA) -- same IEEE arithmetic, different summation order over the columns.
+     * PF_F32 lasso: tcgen05.mma kind::tf32 with every operand split into two tf32 pieces (hi.hi + lo.hi + hi.lo,
+     * FP32 accumulation in TMEM): FP32-faithful to ~1e-6 relative, inside the 1e-5 contract of PF_F32; used for
+     * frontiers of more than 32 nodes (where it is faster than the CUDA cores), or for every size with value 2. */
     PF_OPT_MATVEC_TENSOR = 4,
     /* Host-pointer calls of the pointwise models: 1 (default) = frontiers of up to 432 doubles of theta travel in
      * the kernel parameters, 0 = always through a host->device copy in front of the kernel. */

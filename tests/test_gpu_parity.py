@@ -318,6 +318,34 @@ def test_blasso_tensor_variant_matches_vector_variant(fb, orc, n, p, item_rows, 
     assert rel(pt[0], pv[0]) < 1e-12 and rel(pt[1], pv[1]) < 1e-12
 
 
+@pytest.mark.parametrize("n,p,item_rows,B", [(6000, 100, 500, 16), (5000, 37, 333, 9), (20000, 16, 18000, 64),
+                                              (777, 3, 100, 24), (4096, 1000, 1000, 40), (6000, 100, 500, 3),
+                                              (1000, 64, 50, 1), (30000, 257, 1000, 8)])
+def test_blasso_f32_tcgen05_contraction_is_fp32_faithful(fb, orc, n, p, item_rows, B):
+    """PF_F32 lasso: the contraction runs on the tcgen05 tensor cores as 3xTF32 (hi.hi + lo.hi + hi.lo, FP32 accumulate
+    in TMEM).  Against the oracle on the float-rounded data the error must look like FP32 arithmetic, not like tf32
+    (2^-10): well inside the 1e-5 contract; and it must agree with the CUDA-core FP32 variant to the same level.
+    Shapes cover items shorter than a 128-row tile, items straddling tiles, p not a multiple of 32, every N padding."""
+    from fetching_b200 import models
+    X, y, beta = models.blasso_dataset(n, p, seed=p)
+    th = models.blasso_thetas(beta, B, seed=2, scale=0.02)
+    X32 = X.astype(np.float32).astype(np.float64)
+    want = orc.blasso_frontier(X32, y, th, item_rows)
+    with fb.FrontierEngine.blasso(X, y, item_rows=item_rows, dtype=fb.F32) as e:
+        e.set_option(fb.OPT_MATVEC_TENSOR, 2)   # the tcgen05 path for every B (by default only above 32 nodes)
+        s, q = e.eval_frontier(th)
+        s2, q2 = e.eval_frontier(th)
+        n_items = e.data_size
+        parts = [e.eval_frontier_range(th, a, b - a) for a, b in ((0, n_items // 3), (n_items // 3, n_items))]
+        e.set_option(fb.OPT_MATVEC_TENSOR, 0)
+        sv, qv = e.eval_frontier(th)
+    assert np.array_equal(s, s2) and np.array_equal(q, q2)                       # bit-stable
+    print("tcgen05 3xTF32 vs oracle: %.2e / %.2e; CUDA-core FP32 vs oracle: %.2e" % (rel(s, want[0]), rel(q, want[1]), rel(sv, want[0])))
+    assert rel(s, want[0]) < 8e-6 and rel(q, want[1]) < 1e-5                     # (tf32 alone would be ~1e-3)
+    assert rel(s, sv) < 8e-6 and rel(q, qv) < 1e-5
+    assert rel(parts[0][0] + parts[1][0], s) < 1e-12 and rel(parts[0][1] + parts[1][1], q) < 1e-12
+
+
 def test_blasso_f32_mode(fb, orc):
     from fetching_b200 import models
     X, y, beta = models.blasso_dataset(8000, 200, seed=3)
