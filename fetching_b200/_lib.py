@@ -24,6 +24,7 @@ OPT_NODE_SPLIT = 2
 OPT_PEER_EXCHANGE = 3
 OPT_MATVEC_TENSOR = 4
 OPT_INLINE_THETA = 5
+OPT_RESIDENT = 6
 
 
 class ModelDesc(C.Structure):
@@ -97,6 +98,7 @@ SYMBOLS = {
     "pf_abi_version": (C.c_int, []),
     "pf_last_error": (C.c_char_p, []),
     "pf_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+    "pf_engine_resident_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pf_device_sm_count": (C.c_int, [C.c_int]),
     "pf_debug_math": (C.c_int, [C.c_int, _dp, _dp, C.c_size_t, C.c_int]),
     "pf_debug_fp64_probe": (C.c_int, [C.c_int, _dp]),

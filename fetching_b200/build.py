@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libpfetch.so")
 
-CU_SOURCES = ["pf_pointwise.cu", "pf_matvec.cu", "pf_matvec_tc.cu", "pf_engine.cu", "pf_probe.cu"]
+CU_SOURCES = ["pf_pointwise.cu", "pf_resident.cu", "pf_matvec.cu", "pf_matvec_tc.cu", "pf_engine.cu", "pf_probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

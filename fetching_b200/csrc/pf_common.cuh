@@ -109,7 +109,7 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 // into item totals; an item cut by the CTA boundary is exported as a `head` (its beginning is
 // in an earlier CTA) or `tail` (its end is in a later CTA) partial, and finalize_items() stitches
 // those in CTA order.  Everything is a fixed-order sum: bit-stable for a given geometry.
-// Per-CTA record layout: [S | Q | head | tail][kMaxNodesPerPass].
+// Record layout: [S | Q | head | tail | stitch][kMaxNodesPerPass][kMaxGrid CTAs] (transposed: see ItemOwner::store).
 // ---------------------------------------------------------------------------------------------
 struct ItemOwner {
     double S, Q, run, head, tail;
@@ -161,95 +161,98 @@ struct ItemOwner {
             }
         }
     }
+    // `rec` = part + (index of this CTA): the records are stored TRANSPOSED, [slot][node][CTA], so that the finalizing CTA
+    // reads every (slot, node) row with coalesced loads (see finalize_items)
     __device__ __forceinline__ void store(double* rec, unsigned tid) const {
-        rec[0 * kMaxNodesPerPass + tid] = S;
-        rec[1 * kMaxNodesPerPass + tid] = Q;
-        rec[2 * kMaxNodesPerPass + tid] = head;
-        rec[3 * kMaxNodesPerPass + tid] = tail;
-        rec[4 * kMaxNodesPerPass + tid] = stitch;
+        rec[(size_t) (0 * kMaxNodesPerPass + tid) * kMaxGrid] = S;
+        rec[(size_t) (1 * kMaxNodesPerPass + tid) * kMaxGrid] = Q;
+        rec[(size_t) (2 * kMaxNodesPerPass + tid) * kMaxGrid] = head;
+        rec[(size_t) (3 * kMaxNodesPerPass + tid) * kMaxGrid] = tail;
+        rec[(size_t) (4 * kMaxNodesPerPass + tid) * kMaxGrid] = stitch;
     }
 };
 
-// Finalize, run by the consumer threads of the LAST CTA to finish.  Thread t works for node (t mod BP) as worker
-// (t / BP): it folds the records of CTAs worker, worker+NW, ... -- plain S/Q sums plus, for every CTA in which a cut
-// item ENDS (record slot 4 names the CTA it began in), that item's stitched total
+// Finalize, run by the consumer threads of the LAST CTA to finish.  Records are laid out [slot][node][CTA]
+// (ItemOwner::store).  Warp w folds nodes w, w + nwarps, ...; lane l of it takes the CTAs l, l + 32, ... -- plain S / Q
+// sums plus, for every CTA in which a cut item ENDS (slot 4 names the CTA it began in), that item's stitched total
 //     tail(first CTA of the item) + head(next CTA) + ... + head(this CTA)
-// -- and the NW workers are then combined in worker order.  Fixed order => bit-stable.  The S / Q / stitch loads of a
-// batch of 8 records are all issued before the first use (the tail of every call is this latency-bound loop).
-// `nthreads` consumer threads take part (tid < nthreads); `scratch` holds 2 * nthreads doubles.
+// -- and a butterfly over the lanes adds the 32 partials up.  Fixed order => bit-stable.  Every load of a round (10 CTAs
+// per lane: 2 x 148 CTAs in one round) is issued before the first use and is coalesced over the warp: the tail of every
+// small call is the latency of these rounds (and, with one 8-byte request per thread, was their number: 7 us at B = 1).
+// `nthreads` consumer threads take part (tid < nthreads, whole warps); `scratch` holds 2 * kMaxNodesPerPass doubles.
 // Returns S/Q to threads tid < B.
+template <bool MAY_STITCH = true>
 __device__ __forceinline__ void finalize_items(const double* part, unsigned grid, unsigned long long row_begin,
                                                unsigned long long row_end, unsigned long long rows_per_cta,
                                                unsigned long long item_rows, unsigned tid, unsigned B,
                                                double* scratch, int bar_id, unsigned nthreads, double& S_out,
                                                double& Q_out) {
-    constexpr size_t REC = (size_t) kPartSlots * kMaxNodesPerPass;
-    unsigned BP = 64;
-    if (B <= 32) {
-        BP = 1;
-        while (BP < B) BP <<= 1;
-    }
-    const unsigned NW = nthreads / BP;  // workers per node; threads beyond NW * BP idle
-    const unsigned b = tid % BP, worker = tid / BP;
-    const unsigned bb = b < B ? b : B - 1;
-    double S = 0.0, Q = 0.0;
     unsigned gmax = grid;  // rows_per_cta == 0: every launched CTA wrote a plain (S, Q) record
     if (rows_per_cta) {
         const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
         if (n_cta < gmax) gmax = (unsigned) n_cta;
     }
-    const bool stitching = item_rows > 1 && rows_per_cta;
-    constexpr int BATCH = 8;
-    for (unsigned c = worker < NW ? worker : gmax; c < gmax; c += BATCH * NW) {
-        double s[BATCH], q[BATCH], st[BATCH];
+    const bool stitching = MAY_STITCH && item_rows > 1 && rows_per_cta;
+    const unsigned nwarps = nthreads / 32, warp = tid / 32, lane = tid & 31;
+    constexpr int BATCH = 10;
+    constexpr size_t ROW = (size_t) kMaxGrid, SLOT = (size_t) kMaxNodesPerPass * kMaxGrid;
+    for (unsigned b = warp; b < B; b += nwarps) {
+        const double* const pS = part + (size_t) b * ROW;
+        double S = 0.0, Q = 0.0;
+        for (unsigned c0 = 0; c0 < gmax; c0 += 32 * BATCH) {
+            double s[BATCH], q[BATCH], st[BATCH];
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const unsigned cu = c + u * NW;
-            const bool live = cu < gmax;
-            const double* pr = part + (size_t) (live ? cu : c) * REC + bb;
-            s[u] = ld_cg_f64(pr);
-            q[u] = ld_cg_f64(pr + kMaxNodesPerPass);
-            st[u] = stitching ? ld_cg_f64(pr + 4 * kMaxNodesPerPass) : -1.0;
-            if (!live) {
-                s[u] = q[u] = 0.0;
-                st[u] = -1.0;
+            for (int u = 0; u < BATCH; ++u) {
+                const unsigned c = c0 + u * 32 + lane;
+                const bool live = c < gmax;
+                s[u] = live ? ld_cg_f64(pS + c) : 0.0;
+                q[u] = live ? ld_cg_f64(pS + SLOT + c) : 0.0;
+                st[u] = (stitching && live) ? ld_cg_f64(pS + 4 * SLOT + c) : -1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                S += s[u];
+                Q += q[u];
+            }
+            if (stitching) {
+                // a cut item ends in CTA c when st >= 0: its total is tail(cs) + head(cs + 1) + ... + head(c).  The two
+                // loads every stitch needs are issued for the whole round before any use; CTAs in between exist only
+                // when an item spans more than two CTAs.
+                double tl[BATCH], hd[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const bool stitch = st[u] >= 0.0;
+                    const unsigned c = c0 + u * 32 + lane, cs = stitch ? (unsigned) st[u] : 0u;
+                    tl[u] = stitch ? ld_cg_f64(pS + 3 * SLOT + cs) : 0.0;
+                    hd[u] = stitch ? ld_cg_f64(pS + 2 * SLOT + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    if (st[u] >= 0.0) {
+                        const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[u];
+                        double tot = tl[u];
+                        for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS + 2 * SLOT + k);
+                        tot += hd[u];
+                        S += tot;
+                        Q = fma(tot, tot, Q);
+                    }
+                }
             }
         }
-        // a cut item ends in CTA cu when st >= 0: its total is tail(cs) + head(cs + 1) + ... + head(cu).  The two loads
-        // every stitch needs (tail of the first CTA, head of the last) are issued for the whole batch before any use;
-        // CTAs in between exist only when an item spans more than two CTAs.
-        double tl[BATCH], hd[BATCH];
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const bool stitch = stitching && st[u] >= 0.0;
-            const unsigned cu = c + u * NW, cs = stitch ? (unsigned) st[u] : 0u;
-            tl[u] = stitch ? ld_cg_f64(part + (size_t) cs * REC + 3 * kMaxNodesPerPass + bb) : 0.0;
-            hd[u] = stitch ? ld_cg_f64(part + (size_t) cu * REC + 2 * kMaxNodesPerPass + bb) : 0.0;
+        for (int m = 16; m >= 1; m >>= 1) {
+            S += shfl_xor_f64(S, m);
+            Q += shfl_xor_f64(Q, m);
         }
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            S += s[u];
-            Q += q[u];
-            if (stitching && st[u] >= 0.0) {
-                const unsigned cu = c + u * NW, cs = (unsigned) st[u];
-                double tot = tl[u];
-                for (unsigned k = cs + 1; k < cu; ++k) tot += ld_cg_f64(part + (size_t) k * REC + 2 * kMaxNodesPerPass + bb);
-                tot += hd[u];
-                S += tot;
-                Q = fma(tot, tot, Q);
-            }
+        if (lane == 0) {
+            scratch[b] = S;
+            scratch[kMaxNodesPerPass + b] = Q;
         }
     }
-    scratch[tid] = S;
-    scratch[nthreads + tid] = Q;
     named_bar_sync(bar_id, (int) nthreads);
-    S = 0.0;
-    Q = 0.0;
+    double S = 0.0, Q = 0.0;
     if (tid < B) {
-        for (unsigned w = 0; w < NW; ++w) {
-            S += scratch[w * BP + tid];
-            Q += scratch[nthreads + w * BP + tid];
-        }
+        S = scratch[tid];
+        Q = scratch[kMaxNodesPerPass + tid];
     }
     S_out = S;
     Q_out = Q;

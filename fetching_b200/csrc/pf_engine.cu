@@ -96,9 +96,49 @@ PeerXchg Engine::next_xchg() {
 
 static bool peer_active(const Engine& e) { return e.peer_fused && e.nranks > 1 && !e.node_split; }
 
+// ------------------------------------------------------------------------------------ resident kernel (host side)
+// One resident frontier kernel (pf_resident.cu) can be on a device's SMs at a time -- it fills them.  Whoever launches
+// anything else on that device from this process (another engine, or this engine on a path the resident kernel does
+// not serve) asks it to leave first; work this process knows nothing about simply waits for the idle timeout.
+static Engine* g_res_owner[64] = {};
+
+static bool resident_exited(const Resident& r) {
+    const volatile unsigned long long* st = r.h_words + kResStateWord;
+    return (*st >> 32) == r.epoch && (*st & 1ull);
+}
+
+static void resident_stop(Engine& e) {
+    Resident& r = e.res;
+    if (!r.alive) return;
+    if (!resident_exited(r)) {
+        *(volatile unsigned long long*) (r.h_words + kResCtlWord) = r.epoch;
+        timespec t0, now;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (unsigned long long spins = 1; !resident_exited(r); ++spins) {
+            __builtin_ia32_pause();
+            if ((spins & 0xFFFF) == 0) {
+                if (cudaStreamQuery(e.stream) != cudaErrorNotReady) break;  // gone (or failed: the next call reports it)
+                clock_gettime(CLOCK_MONOTONIC, &now);
+                if ((double) (now.tv_sec - t0.tv_sec) + 1e-9 * (double) (now.tv_nsec - t0.tv_nsec) > 10.0) {
+                    e.wedged = true;  // it will still leave by its idle timeout; nothing more to do from here
+                    break;
+                }
+            }
+        }
+    }
+    r.alive = false;
+    if (g_res_owner[e.device & 63] == &e) g_res_owner[e.device & 63] = nullptr;
+}
+
+static void resident_stop_device(int device) {
+    Engine* o = g_res_owner[device & 63];
+    if (o) resident_stop(*o);
+}
+
 // The engine has one set of scratch buffers (records, ticket, panel, exchange sequence): a launch on a stream other
 // than the previous launch's is ordered behind it.  Costs nothing while the caller stays on one stream.
 static int order_streams(Engine& e, cudaStream_t s) {
+    resident_stop_device(e.device);  // a launched kernel needs the SMs the resident one occupies
     if (e.last_stream != nullptr && e.last_stream != s) {
         if (!e.order_event && cudaEventCreateWithFlags(&e.order_event, cudaEventDisableTiming) != cudaSuccess) {
             set_error("cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -171,6 +211,8 @@ static bool all_identity_cov(const Engine& e, const double* thetas, uint32_t B) 
 static void destroy(Engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    resident_stop(*e);
+    if (g_res_owner[e->device & 63] == e) g_res_owner[e->device & 63] = nullptr;
     if (e->nccl_comm) {
         NcclApi* n = nccl_api();
         if (n && n->CommDestroy) n->CommDestroy((ncclComm_t) e->nccl_comm);
@@ -193,6 +235,9 @@ static void destroy(Engine* e) {
     if (e->h_theta) cudaFreeHost(e->h_theta);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_trace) cudaFreeHost(e->h_trace);
+    if (e->res.h_words) cudaFreeHost(e->res.h_words);
+    cudaFree(e->res.d_relay);
+    cudaFree(e->res.d_ticket);
     if (e->order_event) cudaEventDestroy(e->order_event);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -496,6 +541,7 @@ static bool node_split_fusable(const Engine& e, uint32_t B) {
 static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                                 double* sum, double* sum_sq) {
     PF_CUDA(cudaSetDevice(e.device));
+    resident_stop_device(e.device);
     const uint32_t G = (uint32_t) e.nranks, per = (B + G - 1) / G;
     if (per > kMaxNodesPerPass) {
         set_error("node split: %u nodes per rank exceed one pass (%d)", per, kMaxNodesPerPass);
@@ -570,6 +616,160 @@ static int eval_host_node_split(Engine& e, uint32_t B, const double* thetas, uin
     return PF_OK;
 }
 
+// PF_TRACE=1: ns since CTA 0 entered the kernel (launched kernels) or saw the command (resident kernel)
+static void print_trace(Engine& e) {
+    if (!e.res.alive)
+        cudaStreamSynchronize(e.stream);
+    else {  // a resident kernel stays on the stream; its last marks land within microseconds of the result words
+        timespec ts = {0, 100000};
+        nanosleep(&ts, nullptr);
+    }
+    const unsigned long long* t = e.h_trace;
+    fprintf(stderr, "[pf trace] cta0: prologue %lld first-data %lld scored %lld units-done %lld published %lld | "
+            "last cta: enter %lld folded %lld end %lld (ns)\n", (long long) (t[1] - t[0]), (long long) (t[2] - t[0]),
+            (long long) (t[3] - t[0]), (long long) (t[4] - t[0]), (long long) (t[5] ? t[5] - t[0] : 0),
+            (long long) (t[16] - t[0]), (long long) (t[17] - t[0]), (long long) (t[18] - t[0]));
+    if (t[6]) fprintf(stderr, "[pf trace] mixture exponent form: %s\n", t[6] == 1 ? "factored" : "clamped distance");
+    if (t[7]) fprintf(stderr, "[pf trace] resident kernel: command relayed %lld ns after CTA 0 saw it\n", (long long) (t[7] - t[0]));
+    std::vector<long long> in, out;
+    for (int c = 0; c < kMaxGrid; ++c)
+        if (t[32 + 2 * c]) {
+            in.push_back((long long) (t[32 + 2 * c] - t[0]));
+            out.push_back((long long) (t[33 + 2 * c] - t[0]));
+        }
+    if (!in.empty()) {
+        std::sort(in.begin(), in.end());
+        std::sort(out.begin(), out.end());
+        fprintf(stderr, "[pf trace] %zu CTAs: entry min/med/max %lld/%lld/%lld, published min/med/max %lld/%lld/%lld (ns)\n",
+                in.size(), in.front(), in[in.size() / 2], in.back(), out.front(), out[out.size() / 2], out.back());
+    }
+    if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1' && tr[1] == '1') {  // PF_TRACE=11: every CTA
+        fprintf(stderr, "[pf trace] published(us) by CTA:");
+        for (int c = 0; c < kMaxGrid; ++c)
+            if (t[32 + 2 * c]) fprintf(stderr, " %.1f", (double) (long long) (t[33 + 2 * c] - t[0]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
+    memset(e.h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
+}
+
+// ---- resident path: the whole data set, pointwise models, one GPU, small thetas (see pf_resident.cu)
+static bool resident_ready(Engine& e) {
+    Resident& r = e.res;
+    if (!r.enabled || r.state == 0) return false;
+    if (r.state < 0) {
+        r.state = 0;
+        if (const char* v = getenv("PF_RESIDENT"); v && v[0] == '0') {
+            r.enabled = false;
+            return false;
+        }
+        if (const char* v = getenv("PF_RESIDENT_IDLE_US"); v && atof(v) > 0.0) r.idle_ns = (unsigned long long) (atof(v) * 1e3);
+        if (cudaSetDevice(e.device) != cudaSuccess) return false;
+        if (e.desc.model == PF_MODEL_MIXTURE && !e.f32 && pointwise_table_ptrs(e, &r.exp2_rep, &r.log_mid) != 0) return false;
+        if (resident_configure(e) != 1) return false;
+        if (cudaHostAlloc(&r.h_words, kResHostWords * 8, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&r.d_hcmd, r.h_words, 0) != cudaSuccess ||
+            cudaMalloc(&r.d_relay, (kResRelayDoubles) * 8) != cudaSuccess || cudaMalloc(&r.d_ticket, 64) != cudaSuccess ||
+            cudaMemset(r.d_relay, 0, kResRelayDoubles * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        memset(r.h_words, 0, kResHostWords * 8);
+        r.state = 1;
+    }
+    return true;
+}
+
+static int resident_start(Engine& e, unsigned long long first_seq) {
+    Resident& r = e.res;
+    Engine* o = g_res_owner[e.device & 63];
+    if (o && o != &e) resident_stop(*o);
+    if (r.alive && !resident_exited(r)) resident_stop(e);
+    ++r.epoch;
+    if (resident_launch(e, first_seq) < 0) return PF_ERR_CUDA;
+    r.alive = true;
+    ++r.launches;
+    ++e.launches;
+    e.last_stream = e.stream;
+    g_res_owner[e.device & 63] = &e;
+    return PF_OK;
+}
+
+// one command of nb <= kResMaxNodes nodes
+static int eval_resident(Engine& e, uint32_t nb, const double* th, double* sum, double* sum_sq) {
+    Resident& r = e.res;
+    const unsigned long long seq = next_host_seq(e), tag = (seq & 0xFFFFFFFFull) << 32;
+    if (!r.alive || resident_exited(r) || g_res_owner[e.device & 63] != &e) {
+        const int rc = resident_start(e, seq);
+        if (rc != PF_OK) return rc;
+    }
+    volatile unsigned long long* w = r.h_words;
+    const unsigned n = nb * e.theta_len;
+    for (unsigned i = 0; i < n; ++i) {
+        unsigned long long bits;
+        memcpy(&bits, &th[i], 8);
+        w[1 + 2 * i] = tag | (bits & 0xFFFFFFFFull);
+        w[2 + 2 * i] = tag | (bits >> 32);
+    }
+    unsigned hdr = 1u | (nb << 4);
+    if (e.desc.model == PF_MODEL_NORMAL && !all_identity_cov(e, th, nb)) hdr |= 1u << 12;
+    __atomic_store_n(&r.h_words[0], tag | hdr, __ATOMIC_RELEASE);  // the header last: one poll round finds everything
+    ++r.calls;
+
+    // results: the same self-validating words as the launched host path
+    volatile unsigned long long* o = reinterpret_cast<volatile unsigned long long*>(e.h_out);
+    const unsigned long long want = seq & 0xFFFFFFFFull;
+    double vals[2 * kMaxNodesPerPass];
+    unsigned long long spins = 0;
+    int relaunches = 0;
+    timespec t_start = {0, 0};
+    for (unsigned i = 0; i < 2 * nb; ++i) {
+        for (;;) {
+            const unsigned long long lo = o[2 * i], hi = o[2 * i + 1];
+            if ((lo >> 32) == want && (hi >> 32) == want) {
+                const unsigned long long bits = (hi << 32) | (lo & 0xFFFFFFFFull);
+                memcpy(&vals[i], &bits, 8);
+                break;
+            }
+            __builtin_ia32_pause();
+            if ((++spins & 0x3FF) != 0) continue;
+            if (resident_exited(r)) {
+                // it left (idle timeout, or stopped) -- before it saw this command, unless the words are here by now
+                const unsigned long long lo2 = o[2 * (2 * nb - 1)], hi2 = o[2 * (2 * nb - 1) + 1];
+                if ((lo2 >> 32) == want && (hi2 >> 32) == want) continue;
+                const unsigned reason = (unsigned) ((r.h_words[kResStateWord] >> 8) & 0xFF);
+                if (reason == 3 || ++relaunches > 3) {
+                    set_error("resident kernel left without serving the call (reason %u)", reason);
+                    r.alive = false;
+                    return PF_ERR_CUDA;
+                }
+                const int rc = resident_start(e, seq);  // the command words are still in place: it picks them up
+                if (rc != PF_OK) return rc;
+                continue;
+            }
+            if ((spins & 0x3FFFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(e.stream);
+                if (q != cudaErrorNotReady && q != cudaSuccess) {
+                    set_error("stream error while waiting for the resident kernel: %s", cudaGetErrorString(q));
+                    r.alive = false;
+                    return PF_ERR_CUDA;
+                }
+                timespec now;
+                clock_gettime(CLOCK_MONOTONIC, &now);
+                if (t_start.tv_sec == 0 && t_start.tv_nsec == 0) t_start = now;
+                if ((double) (now.tv_sec - t_start.tv_sec) + 1e-9 * (double) (now.tv_nsec - t_start.tv_nsec) > host_timeout_s()) {
+                    e.wedged = true;
+                    set_error("the resident kernel delivered nothing within %.0f s (PF_HOST_TIMEOUT_S): engine marked unusable",
+                              host_timeout_s());
+                    return PF_ERR_CUDA;
+                }
+            }
+        }
+    }
+    memcpy(sum, vals, (size_t) nb * 8);
+    memcpy(sum_sq, vals + nb, (size_t) nb * 8);
+    return PF_OK;
+}
+
 static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first_item, uint64_t n_items,
                      const uint64_t* order, double* sum, double* sum_sq) {
     if (e.wedged) {
@@ -587,6 +787,19 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
         return PF_OK;
     }
     PF_CUDA(cudaSetDevice(e.device));
+    if (!order && e.nranks <= 1 && first_item == 0 && n_items == e.n_items && e.theta_len <= (uint32_t) kResThetaDoubles &&
+        (e.desc.model == PF_MODEL_NORMAL || e.desc.model == PF_MODEL_MIXTURE) && resident_ready(e)) {
+        uint32_t per = (uint32_t) kResThetaDoubles / e.theta_len;  // nodes per command
+        if (per > e.res.max_nodes) per = e.res.max_nodes;
+        for (uint32_t b0 = 0; b0 < B; b0 += per) {
+            const uint32_t nb = B - b0 < per ? B - b0 : per;
+            const int r = eval_resident(e, nb, thetas + (size_t) b0 * e.theta_len, sum + b0, sum_sq + b0);
+            if (r != PF_OK) return r;
+        }
+        if (e.h_trace) print_trace(e);
+        return PF_OK;
+    }
+    resident_stop_device(e.device);  // everything below launches kernels
     for (uint32_t b0 = 0; b0 < B; b0 += e.max_frontier) {
         const uint32_t nb = B - b0 < e.max_frontier ? B - b0 : e.max_frontier;
         const double* th = thetas + (size_t) b0 * e.theta_len;
@@ -628,34 +841,7 @@ static int eval_host(Engine& e, uint32_t B, const double* thetas, uint64_t first
             r = wait_words(e, 2 * nb, e.done_seq, vals);
             if (r != PF_OK) return r;
             if (peer_status(e) != PF_OK) return PF_ERR_NCCL;
-            if (e.h_trace) {  // PF_TRACE=1: ns since CTA 0 entered the kernel
-                cudaStreamSynchronize(e.stream);
-                const unsigned long long* t = e.h_trace;
-                fprintf(stderr, "[pf trace] cta0: prologue %lld first-data %lld scored %lld units-done %lld published %lld | "
-                        "last cta: enter %lld folded %lld end %lld (ns)\n", (long long) (t[1] - t[0]), (long long) (t[2] - t[0]),
-                        (long long) (t[3] - t[0]), (long long) (t[4] - t[0]), (long long) (t[5] ? t[5] - t[0] : 0),
-                        (long long) (t[16] - t[0]), (long long) (t[17] - t[0]), (long long) (t[18] - t[0]));
-                if (t[6]) fprintf(stderr, "[pf trace] mixture exponent form: %s\n", t[6] == 1 ? "factored" : "clamped distance");
-                std::vector<long long> in, out;
-                for (int c = 0; c < kMaxGrid; ++c)
-                    if (t[32 + 2 * c]) {
-                        in.push_back((long long) (t[32 + 2 * c] - t[0]));
-                        out.push_back((long long) (t[33 + 2 * c] - t[0]));
-                    }
-                if (!in.empty()) {
-                    std::sort(in.begin(), in.end());
-                    std::sort(out.begin(), out.end());
-                    fprintf(stderr, "[pf trace] %zu CTAs: entry min/med/max %lld/%lld/%lld, published min/med/max %lld/%lld/%lld (ns)\n",
-                            in.size(), in.front(), in[in.size() / 2], in.back(), out.front(), out[out.size() / 2], out.back());
-                }
-                if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1' && tr[1] == '1') {  // PF_TRACE=11: every CTA
-                    fprintf(stderr, "[pf trace] published(us) by CTA:");
-                    for (int c = 0; c < kMaxGrid; ++c)
-                        if (t[32 + 2 * c]) fprintf(stderr, " %.1f", (double) (long long) (t[33 + 2 * c] - t[0]) * 1e-3);
-                    fprintf(stderr, "\n");
-                }
-                memset(e.h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
-            }
+            if (e.h_trace) print_trace(e);
             memcpy(sum + b0, vals, (size_t) nb * 8);
             memcpy(sum_sq + b0, vals + nb, (size_t) nb * 8);
             continue;
@@ -735,6 +921,14 @@ double* pf_engine_theta_buffer(pf_engine* pe, uint64_t* capacity_doubles) {
 
 uint64_t pf_engine_launch_count(const pf_engine* e) { return e ? reinterpret_cast<const Engine*>(e)->launches : 0; }
 
+int pf_engine_resident_stats(const pf_engine* pe, uint64_t* calls, uint64_t* launches) {
+    if (!pe) return 0;
+    const Engine& e = *reinterpret_cast<const Engine*>(pe);
+    if (calls) *calls = e.res.calls;
+    if (launches) *launches = e.res.launches;
+    return e.res.state == 1 && e.res.enabled ? 1 : 0;
+}
+
 int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
     if (!pe) return PF_ERR_INVALID;
     Engine& e = *reinterpret_cast<Engine*>(pe);
@@ -743,6 +937,10 @@ int pf_engine_set_option(pf_engine* pe, int option, int64_t value) {
         case PF_OPT_NODE_SPLIT: e.node_split = value != 0; return PF_OK;
         case PF_OPT_MATVEC_TENSOR: e.mv_tensor = value != 0; e.mv_tensor_force = value == 2; return PF_OK;
         case PF_OPT_INLINE_THETA: e.allow_inline_theta = value != 0; return PF_OK;
+        case PF_OPT_RESIDENT:
+            e.res.enabled = value != 0;
+            if (!e.res.enabled) pf::resident_stop(e);
+            return PF_OK;
         case PF_OPT_PEER_EXCHANGE:
             if (value != 0 && !e.peer_attached) {
                 pf::set_error("PF_OPT_PEER_EXCHANGE: no peer buffers attached (pf_engine_peer_attach)");

@@ -36,7 +36,7 @@ struct PeerXchg {
 struct PointwiseArgs {
     const void* data;       // device, row-major [rows][dim] of T, 256-byte aligned, padded
     const double* theta;    // device [B][theta_len]
-    double* part;           // device [grid][kPartSlots][64]
+    double* part;           // device [kPartSlots][64][kMaxGrid]: per-CTA records, transposed (ItemOwner::store)
     double* out;            // device [2][B]
     unsigned int* ticket;   // device, zero between launches
     unsigned long long row_begin, row_end;  // rows to score (whole items)
@@ -90,6 +90,50 @@ struct MatvecArgs {
     unsigned long long* trace;        // see PointwiseArgs
 };
 
+// ---- resident frontier kernel (pf_resident.cu): launched once, driven through a doorbell in mapped host memory
+constexpr int kResMaxNodes = 32;                              // nodes per command (larger frontiers: several commands)
+constexpr int kResThetaDoubles = 512;                         // theta doubles per command (32 nodes of the K = 8, d = 2 mixture)
+constexpr int kResCmdWords = 1 + 2 * kResThetaDoubles;        // header + two words per theta double
+constexpr int kResCtlWord = 1040;                             // stop request: the epoch of the launch to stop
+constexpr int kResStateWord = 1048;                           // written by the kernel when it leaves: epoch << 32 | reason << 8 | 1
+constexpr int kResHostWords = 1056;
+constexpr int kResRelayDoubles = kResCmdWords + 7;            // relay block in device memory: the command words as CTA 0 forwards them
+
+struct ResidentArgs {
+    const void* data;
+    double* part;
+    double* out;                       // device alias of the mapped result words (Engine::d_hout)
+    unsigned long long* ticket;        // device, zero at launch, monotonic afterwards
+    const unsigned long long* h_cmd;   // device alias of the mapped command words {tag << 32 | payload}
+    const unsigned long long* h_ctl;   // mapped: stop request
+    unsigned long long* h_state;       // mapped: exit notice
+    unsigned long long* d_relay;       // device: the command words of the current call, forwarded by CTA 0 (same format)
+    const double* exp2_rep;            // device tables of the FP64 mixture loop (pf_math.cuh), or nullptr
+    const double* log_mid;
+    unsigned long long row_end, item_rows;
+    unsigned int rows_per_cta, theta_len, K, cap_bytes;
+    unsigned long long first_seq, epoch, idle_ns;
+    unsigned long long* trace;
+    double xmax[8];
+};
+
+struct Resident {
+    int state = -1;              // -1: not looked at yet, 0: not eligible, 1: eligible (geometry below is valid)
+    bool enabled = true;         // PF_OPT_RESIDENT / PF_RESIDENT
+    bool alive = false;          // a launch is (as far as the host knows) on the SMs
+    const void* kern = nullptr;
+    unsigned grid = 0, rows_per_cta = 0, cap_bytes = 0, max_nodes = 32;  // max_nodes: nodes one command may carry
+    size_t smem = 0;
+    unsigned long long epoch = 0, idle_ns = 2000000ull;
+    unsigned long long* h_words = nullptr;  // pinned + mapped: command words, control word, state word
+    unsigned long long* d_hcmd = nullptr;   // device alias
+    unsigned long long* d_relay = nullptr;
+    unsigned long long* d_ticket = nullptr;
+    const double* exp2_rep = nullptr;
+    const double* log_mid = nullptr;
+    uint64_t calls = 0, launches = 0;
+};
+
 struct Engine {
     pf_model_desc desc;
     int device = 0;
@@ -110,7 +154,7 @@ struct Engine {
     double* d_resp = nullptr;    // lasso response (always double)
     double* d_theta = nullptr;   // [max_frontier][theta_len]
     double* d_out = nullptr;     // [2][max_frontier]
-    double* d_part = nullptr;    // [kMaxGrid][kPartSlots][64]
+    double* d_part = nullptr;    // [kPartSlots][64][kMaxGrid]
     void* d_betaT = nullptr;     // matvec coefficient panel
     unsigned long long* d_order = nullptr;  // [max_frontier][2] StrideIndex (stride, start) per node
     unsigned int* d_ticket = nullptr;
@@ -151,6 +195,7 @@ struct Engine {
     cudaEvent_t order_event = nullptr;
     cudaStream_t last_stream = nullptr;
     bool wedged = false;  // a frontier kernel never completed (wait_words timed out): every later call fails
+    Resident res;
 };
 
 // launchers (defined in the .cu files); return the number of kernels launched or <0 on error
@@ -168,6 +213,9 @@ int launch_exchange_only(Engine& e, uint32_t B, double* d_out, cudaStream_t s, u
 // PF_F32 lasso on tcgen05 (pf_matvec_tc.cu): fills the tile geometry of `a`, launches the panel prep + frontier kernels
 int launch_matvec_tc32(Engine& e, MatvecArgs& a, const double* d_theta, cudaStream_t s);
 int make_tmap(Engine& e, unsigned tile_rows, CUtensorMap* out);  // cached 2-D tensor map of the matrix (pf_matvec.cu)
+int resident_configure(Engine& e);                                  // pf_resident.cu: 1 = the data set fits shared memory
+int resident_launch(Engine& e, unsigned long long first_seq);       // pf_resident.cu
+int pointwise_table_ptrs(Engine& e, const double** exp2_rep, const double** log_mid);  // pf_pointwise.cu
 uint32_t pointwise_max_frontier(const Engine& e);
 int ensure_exp_table_for(Engine& e);  // uploads the mixture loop's exp table to e.device (once per device)
 bool pointwise_supported(const Engine& e);

@@ -353,7 +353,7 @@ __device__ const double kLogTab[512] = {
     0.5, 0.0,
 };
 // 1/(2i+1), i = 1..10: odd atanh series
-__constant__ double kAtanhC[10] = {1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0,  1.0 / 9.0,  1.0 / 11.0,
+static __constant__ double kAtanhC[10] = {1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0,  1.0 / 9.0,  1.0 / 11.0,
                                    1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0};
 constexpr double kNegHalfLog2e = -0.72134752044448170368;  // -log2(e)/2
 constexpr double kLog2e = 1.44269504088896340736;
@@ -462,10 +462,10 @@ constexpr int kExpArgClampHi = 0x40960000;         // high word of 1408.0: -e/2 
 // ptxas re-materialises with two MOVs per iteration), and the leading coefficient B3 = ln2^3/6 lives in the table.
 constexpr double kExpQ2 = 4.328085122666891, kExpQ1 = 12.488213886033646, kExpQ0 = 18.016684242941434;
 // filled once per device by the host (pf_pointwise.cu: ensure_exp_table): long-double B3 2^(j/2048), high word - (j << 9)
-__device__ __align__(16) double g_exp2_big[kExpBigSize];
+static __device__ __align__(16) double g_exp2_big[kExpBigSize];
 // ... and the log table as log_pos_fast_k wants it ({1/c_j doubled for j >= kLogTabFirstHalf, log c_j}), so that both
 // tables reach shared memory by one TMA bulk copy each instead of ten dependent loads per thread
-__device__ __align__(16) double g_log_adj[512];
+static __device__ __align__(16) double g_log_adj[512];
 
 template <int G>
 __device__ __forceinline__ void mix_exp_accumulate(double (&e)[G], double& lp0, double& lp1, unsigned tab_s) {
@@ -561,7 +561,7 @@ constexpr long double kExp3B3 = 0.05550411502275755523220807L;  // leading coeff
 constexpr double kRintMagicRep = 26388279066624.0;              // 1.5 * 2^44: rint(256 z) lands in the low word
 constexpr double kFactoredLimit = 512.0;  // bound on |z| under which the factored form is used
 // filled once per device by the host (ensure_exp_table): [256][16] copies of (long-double B3 2^(j/256), high word - (j << 12))
-__device__ __align__(128) double g_exp2_rep[kExpRepSize * kExpRepCopies];
+static __device__ __align__(128) double g_exp2_rep[kExpRepSize * kExpRepCopies];
 
 // one component: t = z + magic already formed; lp += 2^k T[j] (g^3 + Q2 g^2 + Q1 g + Q0).  `tab_l` is the shared-memory
 // address of THIS LANE's copy of entry 0 (table base + 8 (lane mod 16)); entries are 128 bytes apart.
@@ -628,7 +628,7 @@ __device__ __forceinline__ void mix_exp_accumulate_e(double (&e)[G], double& lp0
 // log(1) = 0 exactly: |r| <= 2^-9 everywhere (with c = 1, r reaches 2^-8 and r^5/5 = 1.8e-13); log(1) comes out as
 // ~1e-17 instead of 0, which a sum over rows does not see.  Same addressing and same doubling of 1/c_j for
 // j >= kLogTabFirstHalf as log_pos_fast_k.
-__device__ __align__(16) double g_log_mid[512];
+static __device__ __align__(16) double g_log_mid[512];
 constexpr double kLogC3 = 0.33333325386047363281;  // 0x3FD5555500000000 ~ 1/3 (its term is <= 2.5e-9: error 6e-16)
 __device__ __forceinline__ double log_pos_acc(double x, unsigned ltab_s, int& nacc) {
     const int hi = __double2hiint(x);

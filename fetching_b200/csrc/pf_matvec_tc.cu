@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
             }
         }
         trace_mark(a.trace, 0, 4, tr0);  // all tiles done
-        double* rec = a.part + (size_t) blockIdx.x * kPartSlots * kMaxNodesPerPass;
+        double* rec = a.part + blockIdx.x;  // column of this CTA in the [slot][node][CTA] records
         if ((unsigned) tid < B) {
             own.finish(r0, r1, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows);
             own.store(rec, tid);

@@ -167,6 +167,13 @@ class FrontierEngine:
     def launch_count(self) -> int:
         return int(self._lib.pf_engine_launch_count(self._h))
 
+    @property
+    def resident_stats(self):
+        """(eligible, calls served by the resident kernel, times it was launched) -- pf_engine_resident_stats."""
+        calls, launches = C.c_uint64(0), C.c_uint64(0)
+        ok = self._lib.pf_engine_resident_stats(self._h, C.byref(calls), C.byref(launches))
+        return bool(ok), int(calls.value), int(launches.value)
+
     def close(self) -> None:
         if self._h:
             self._lib.pf_engine_destroy(self._h)

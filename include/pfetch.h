@@ -284,7 +284,15 @@ enum pf_option {
     PF_OPT_MATVEC_TENSOR = 4,
     /* Host-pointer calls of the pointwise models: 1 (default) = frontiers of up to 432 doubles of theta travel in
      * the kernel parameters, 0 = always through a host->device copy in front of the kernel. */
-    PF_OPT_INLINE_THETA = 5
+    PF_OPT_INLINE_THETA = 5,
+    /* Host-pointer calls over ALL items of a pointwise model (normal target, mixture) whose data set fits the shared
+     * memory of the GPU (about 1.1e6 rows of two doubles): 1 (default) = served by the RESIDENT frontier kernel --
+     * launched once, rows / tables / barriers kept in shared memory between calls, driven through a doorbell in mapped
+     * host memory (thetas in, sums out as self-validating words; no launch, no copy, no synchronise per call).  It
+     * leaves the SMs when this process launches anything else on the device, when the engine is destroyed, or after
+     * 2 ms without a call (PF_RESIDENT_IDLE_US), and comes back with the next call.  0 = every call launches a kernel.
+     * Results are bit-identical either way.  The environment variable PF_RESIDENT=0 changes the default. */
+    PF_OPT_RESIDENT = 6
 };
 PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 
@@ -292,6 +300,9 @@ PF_API int pf_engine_set_option(pf_engine* e, int option, int64_t value);
 PF_API int pf_abi_version(void);
 PF_API const char* pf_last_error(void);                 /* thread-local text of the last failure */
 PF_API uint64_t pf_engine_launch_count(const pf_engine* e); /* kernels launched by this engine so far */
+/* Calls served by the resident frontier kernel so far (*calls) and how often it was launched (*launches); either
+ * pointer may be NULL.  Returns 1 if the engine's data set qualifies for it (known after the first eligible call). */
+PF_API int pf_engine_resident_stats(const pf_engine* e, uint64_t* calls, uint64_t* launches);
 PF_API int pf_device_sm_count(int device);
 /* Diagnostics: apply the engine's device exp(-x/2) (which = 0: double, 2: float; 5: the mixture loop's
  * 2048-entry degree-3 version; 9: its degree-2 successor, the clamped loop's) or log(x) (1: double, 3: float, 4: table

@@ -112,9 +112,12 @@ int main(int argc, char** argv) {
     typedef pf::host::FrontierCommunicator<JobTree, NormalSampler<2>, RefTypes, EngineEvaluator, NoTrace> Comm;
     Comm comm(*tree, executor, eval, (int) workers, pf_engine_data_size(engine), &trace);
     tree->run_master<Comm, Comm::Request, Comm::Status>(comm, JobTree::run_behavior().quiet(true));
-    printf("# levels %zu engine_calls %zu nodes_scored %zu max_batch %zu kernel_launches %llu\n", tree->completed_depth(),
-           comm.stats().engine_calls, comm.stats().nodes_scored, comm.stats().max_batch,
-           (unsigned long long) pf_engine_launch_count(engine));
+    // one kernel pass per burst: a launch, or a command served by the resident frontier kernel (launched once)
+    uint64_t res_calls = 0, res_launches = 0;
+    pf_engine_resident_stats(engine, &res_calls, &res_launches);
+    printf("# levels %zu engine_calls %zu nodes_scored %zu max_batch %zu kernel_launches %llu resident_calls %llu resident_launches %llu\n",
+           tree->completed_depth(), comm.stats().engine_calls, comm.stats().nodes_scored, comm.stats().max_batch,
+           (unsigned long long) pf_engine_launch_count(engine), (unsigned long long) res_calls, (unsigned long long) res_launches);
     fflush(stdout);
     const int rc = eval.status;
     pf_engine_destroy(engine);
