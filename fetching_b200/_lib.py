@@ -105,6 +105,7 @@ SYMBOLS = {
     "pf_debug_dmma_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_issue_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_rf_probe": (C.c_int, [C.c_int, _dp]),
+    "pf_debug_dfma_dmma_probe": (C.c_int, [C.c_int, _dp]),
     "pf_debug_launch_probe": (C.c_int, [C.c_int, _dp]),
     "pf_engine_theta_buffer": (_dp, [C.c_void_p, C.POINTER(C.c_uint64)]),
 }

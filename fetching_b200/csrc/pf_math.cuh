@@ -546,7 +546,7 @@ __device__ __forceinline__ double log_pos_fast_k(double x, unsigned ltab_s) {
 //         z_k = A_k + B_k . x,   A_k = -log2(e)/2 |theta_k|^2,   B_k = log2(e) theta_k   (per node, staged once per call):
 //     d FMAs per component instead of d subtractions + d multiply-adds + the scaling.  K = 8, d = 2: 9 FP64 instructions
 //     per component (2 z, 3 range reduction, 3 polynomial, 1 accumulate) against 11 before.  Rounding: z carries an absolute
-//     error of a few 2^-53 max(|A_k|, |B_k.x|); the kernel takes this path only when  |A_k| + sum_j |B_kj| max|x_j| <= 512
+//     error of a few 2^-53 max(|A_k|, |B_k.x|); the kernel takes this path only when  |A_k| + sum_j |B_kj| max|x_j| <= 500
 //     for every component of every node (theta against the data set's bounding box, checked while theta is staged), which
 //     bounds the error of a term by 2e-13 relative in the worst corner and ~1e-15 for data like the benchmark's, keeps
 //     every 2^z a normal number, so no clamp, no slow path and no per-row range test are needed; anything else (far
@@ -559,7 +559,8 @@ constexpr int kExpRepBits = 8, kExpRepSize = 1 << kExpRepBits, kExpRepCopies = 1
 constexpr double kExp3Q2 = 4.3280852879260374, kExp3Q1 = 12.488212455522227, kExp3Q0 = 18.016682179149544;
 constexpr long double kExp3B3 = 0.05550411502275755523220807L;  // leading coefficient (in the table)
 constexpr double kRintMagicRep = 26388279066624.0;              // 1.5 * 2^44: rint(256 z) lands in the low word
-constexpr double kFactoredLimit = 512.0;  // bound on |z| under which the factored form is used
+constexpr double kFactoredLimit = 500.0;  // bound on |z| under which the factored form is used (the product of two row
+                                          // sums, each in [2^-500, 32 * 2^500], stays a normal number: PF_MIX_PROD)
 // filled once per device by the host (ensure_exp_table): [256][16] copies of (long-double B3 2^(j/256), high word - (j << 12))
 static __device__ __align__(128) double g_exp2_rep[kExpRepSize * kExpRepCopies];
 

@@ -34,6 +34,21 @@ namespace pf {
 #ifndef PF_MIX_TWO_ACC
 #define PF_MIX_TWO_ACC 0  // factored mixture form: two partial sums per row (1) or a single accumulation chain (0)
 #endif
+// PF_MIX_PROD (factored form): no log per row -- the row sums are MULTIPLIED into a running product whose binary exponent is
+// moved to an integer after every multiplication (one DMUL + SHF + IADD3 + LOP3 per row instead of 7 FP64 + 8 other for a
+// table-driven log), and the log of the product is taken once per tile and lane.  Every row sum is a normal number in
+// [2^-kFactoredLimit, K 2^kFactoredLimit] (kFactoredLimit = 500), so neither the product of two row sums nor its product with a mantissa in [1, 2) can leave
+// the normal range.  Error: half an ulp per multiplication, i.e. <= 32 * 1.1e-16 absolute on a lane's tile sum
+// (the per-row logs carried 5.7e-15 of truncation EACH).
+#ifndef PF_MIX_PROD
+#define PF_MIX_PROD 1
+#endif
+// PF_MIX_PAIR (factored form, two rows per iteration): the two rows walk the components TOGETHER -- A_k / B_k are read once
+// for both, consecutive DFMAs share two of their three register operands (operand-reuse cache: a DFMA with three fresh
+// register pairs costs 2.8 issue cycles instead of 2, scripts/fp64_probe.py), 4 components x 2 rows in flight.
+#ifndef PF_MIX_PAIR
+#define PF_MIX_PAIR 1
+#endif
 constexpr int PW_CONSUMER_WARPS = PF_PW_WARPS;  // 8 warps = 256 threads: two CTAs per SM fit at up to 128 registers
 constexpr int PW_CONSUMERS = PW_CONSUMER_WARPS * 32;
 // PF_PW_FOLD: no dedicated producer warp -- lane 0 of consumer warp 0 issues the TMA copies between its rows.
@@ -214,16 +229,27 @@ struct MixtureModel {
     static __host__ __device__ constexpr unsigned staged_len(unsigned theta_len) {
         return FACTORED ? theta_len + K : theta_len;
     }
+    static constexpr bool PROD = FACTORED && (PF_MIX_PROD != 0);      // running product instead of a log per row
+    static constexpr bool PAIR = FACTORED && (PF_MIX_PAIR != 0) && RB == 2 && (K % 4 == 0) && (D % 2 == 0);
     struct RowState {
         unsigned redo;  // slow_path_accumulate() key, tested once per tile
-        int nacc;       // sum of the rows' binary exponents (log_pos_acc)
+        int nacc;       // sum of the rows' binary exponents (log_pos_acc / product form)
         double xsq;     // sum of the rows' |x|^2 (factored form)
+        double prod;    // product form: mantissa in [1, 2) of the product of the row sums seen so far
         __device__ __forceinline__ void reset() {
             redo = 0u;
             nacc = 0;
             xsq = 0.0;
+            prod = 1.0;
         }
     };
+    // prod <- prod * v, exponent moved into nacc (v a positive normal number; prod stays in [1, 2))
+    static __device__ __forceinline__ void prod_accumulate(RowState& st, double v) {
+        const double p = st.prod * v;
+        const int hi = __double2hiint(p);
+        st.nacc += (hi >> 20) - 1023;  // SHF + IADD3
+        st.prod = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(p));  // one LOP3
+    }
     struct Node {
         const CT* th;
         unsigned tab_s;       // shared-memory ADDRESS of the exp table (FP64: 2048 adjusted entries; float: unused)
@@ -334,6 +360,53 @@ struct MixtureModel {
             return lp;
         }
     }
+    // two rows at once (PAIR): row sums into lpa / lpb
+    static __device__ __forceinline__ void mix_sum2(const Node& nd, const CT (&xa)[D], const CT (&xb)[D], double& lpa, double& lpb) {
+        constexpr int G2 = 4;
+        lpa = 0.0;
+        lpb = 0.0;
+        const unsigned th_s = smem_u32(nd.th);
+#pragma unroll
+        for (int k0 = 0; k0 < K; k0 += G2) {
+            double z[2 * G2], a[G2];
+#pragma unroll
+            for (int g = 0; g < G2; g += 2)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[g]), "=d"(a[g + 1]) : "r"(th_s + (unsigned) ((K * D + k0 + g) * 8)));
+#pragma unroll
+            for (int g = 0; g < G2; ++g) {
+                double b[D];
+#if PF_MIX_RELOAD >= 2
+#pragma unroll
+                for (int j = 0; j < D; j += 2)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b[j]), "=d"(b[j + 1]) : "r"(th_s + (unsigned) (((k0 + g) * D + j) * 8)));
+#else
+                load_row<double, D, double>(reinterpret_cast<const unsigned char*>(nd.th + (k0 + g) * D), b);
+#endif
+                z[2 * g] = fma(b[0], xa[0], a[g]);
+                z[2 * g + 1] = fma(b[0], xb[0], a[g]);
+#pragma unroll
+                for (int j = 1; j < D; ++j) {
+                    z[2 * g] = fma(b[j], xa[j], z[2 * g]);
+                    z[2 * g + 1] = fma(b[j], xb[j], z[2 * g + 1]);
+                }
+            }
+            mix_exp_accumulate_z<2 * G2, true>(z, lpa, lpb, nd.tab_s);  // even chains -> lpa, odd -> lpb
+        }
+    }
+    // PAIR hot loop body: both rows' contributions go into the lane state (product form) or come back summed
+    static __device__ __forceinline__ double pair_fast(const Node& nd, const CT (&xa)[D], const CT (&xb)[D], RowState& st) {
+        double lpa, lpb;
+        mix_sum2(nd, xa, xb, lpa, lpb);
+#pragma unroll
+        for (int j = 0; j < D; ++j) st.xsq = fma(xa[j], xa[j], st.xsq);
+#pragma unroll
+        for (int j = 0; j < D; ++j) st.xsq = fma(xb[j], xb[j], st.xsq);
+        if constexpr (PROD) {
+            prod_accumulate(st, lpa * lpb);  // >= 2^-2 kFactoredLimit: normal
+            return 0.0;
+        } else
+            return log_pos_acc(lpa, nd.ltab_s, st.nacc) + log_pos_acc(lpb, nd.ltab_s, st.nacc);
+    }
     // Hot loop: branch free.  Clamped form: a row whose sum left the fast path's range (every component ~40 sigma away,
     // or non-finite input) contributes garbage here and raises `st.redo`; the caller then DISCARDS this lane's sums of
     // the tile and re-walks its rows with rowlp_redo (fast value, or the library for the rows out of range), so
@@ -345,7 +418,11 @@ struct MixtureModel {
         if constexpr (FACTORED) {
 #pragma unroll
             for (int j = 0; j < D; ++j) st.xsq = fma(x[j], x[j], st.xsq);
-            return log_pos_acc(lp, nd.ltab_s, st.nacc);
+            if constexpr (PROD) {
+                prod_accumulate(st, lp);
+                return 0.0;
+            } else
+                return log_pos_acc(lp, nd.ltab_s, st.nacc);
         } else {
             slow_path_accumulate(st.redo, lp);  // the value is NOT masked (see above)
             if constexpr (BIG_EXP_TABLE)
@@ -358,8 +435,12 @@ struct MixtureModel {
         if constexpr (HAS_REDO) return acc_needs_slow_path(st.redo);
         return false;
     }
-    static __device__ __forceinline__ void tile_fixup(const RowState& st, double& acc) {
-        if constexpr (FACTORED)
+    static __device__ __forceinline__ void tile_fixup(const Node& nd, const RowState& st, double& acc) {
+        if constexpr (PROD) {  // acc carries nothing yet: the tile's rows live in (prod, nacc, xsq)
+            int n = st.nacc;
+            const double lg = log_pos_acc(st.prod, nd.ltab_s, n);
+            acc = log_n_times_ln2(n, fma(-0.5, st.xsq, lg));
+        } else if constexpr (FACTORED)
             acc = log_n_times_ln2(st.nacc, fma(-0.5, st.xsq, acc));
         else if constexpr (BIG_EXP_TABLE)
             acc = log_n_times_ln2(st.nacc, acc);
@@ -479,6 +560,26 @@ template <class M>
 struct BigExpTable<M, std::enable_if_t<M::BIG_EXP_TABLE>> { static constexpr bool value = true; };
 template <class M>
 __host__ __device__ constexpr bool big_exp_table() { return BigExpTable<M>::value; }
+template <class M, class = void>
+struct ProdRows { static constexpr bool value = false; };
+template <class M>
+struct ProdRows<M, std::enable_if_t<M::PROD>> { static constexpr bool value = true; };
+template <class M>
+__host__ __device__ constexpr bool prod_rows() { return ProdRows<M>::value; }
+template <class M, class = void>
+struct PairRows { static constexpr bool value = false; };
+template <class M>
+struct PairRows<M, std::enable_if_t<M::PAIR>> { static constexpr bool value = true; };
+template <class M>
+__host__ __device__ constexpr bool pair_rows() { return PairRows<M>::value; }
+
+template <class M, class Node, class X, class St>
+__device__ __forceinline__ double pair_call(const Node& nd, const X& xa, const X& xb, St& st) {
+    if constexpr (pair_rows<M>())
+        return M::pair_fast(nd, xa, xb, st);
+    else
+        return 0.0;
+}
 
 // per-warp slots of the block reductions: [buffer][warp][32 * NPL nodes]; the finalize step reuses the area as scratch
 // (finalize_items: 2 doubles per thread; peer_allreduce: 2 * kMaxNodesPerPass)
@@ -688,18 +789,26 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
                 CT x[RB][DIM];
 #pragma unroll
                 for (unsigned u = 0; u < RB; ++u) load_row<T, DIM, CT>(base + (size_t) (j + u * nslots) * RB_BYTES, x[u]);
-#pragma unroll
-                for (unsigned u = 0; u < RB; ++u)
+                if constexpr (RB == 2 && pair_rows<M>()) {
 #pragma unroll
                     for (int n = 0; n < NPL; ++n) {
-                        double v;
-                        if constexpr (M::HAS_REDO || M::HAS_FIXUP)
-                            v = (double) M::rowlp_fast(nd[n], x[u], st[n]);
-                        else
-                            v = (double) M::rowlp(nd[n], x[u]);
-                        accS[n] += v;
-                        if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
+                        const double v = pair_call<M>(nd[n], x[0], x[1], st[n]);
+                        if constexpr (!prod_rows<M>()) accS[n] += v;
                     }
+                } else {
+#pragma unroll
+                    for (unsigned u = 0; u < RB; ++u)
+#pragma unroll
+                        for (int n = 0; n < NPL; ++n) {
+                            double v;
+                            if constexpr (M::HAS_REDO || M::HAS_FIXUP)
+                                v = (double) M::rowlp_fast(nd[n], x[u], st[n]);
+                            else
+                                v = (double) M::rowlp(nd[n], x[u]);
+                            if constexpr (!prod_rows<M>()) accS[n] += v;
+                            if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
+                        }
+                }
             }
         };
         if constexpr (M::ITEM1)
@@ -720,7 +829,7 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
                     v = (double) M::rowlp_fast(nd[n], x, st[n]);
                 else
                     v = (double) M::rowlp(nd[n], x);
-                accS[n] += v;
+                if constexpr (!prod_rows<M>()) accS[n] += v;
                 if constexpr (M::ITEM1) accQ[n] = fma(v, v, accQ[n]);
             }
         }
@@ -744,7 +853,7 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
         }
         if constexpr (M::HAS_FIXUP) {
 #pragma unroll
-            for (int n = 0; n < NPL; ++n) M::tile_fixup(st[n], accS[n]);
+            for (int n = 0; n < NPL; ++n) M::tile_fixup(nd[n], st[n], accS[n]);
         }
         if constexpr (M::ITEM1) {
             if constexpr (!RES) {

@@ -313,6 +313,76 @@ extern "C" PF_API int pf_debug_rf_probe(int device, double* out3) {
     return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
 }
 
+// Do DFMA (FP64 pipe) and DMMA m8n8k4 (tensor pipe) overlap?  NF two-register DFMAs (8 chains) and ND DMMAs with fresh
+// (zero) accumulators per block, 16 warps per SM.  out[i] = microseconds per 1000 blocks per warp-slot for
+// (NF, ND) = (16,0) (0,2) (0,4) (16,1) (16,2) (16,4) (32,4) (8,4).
+namespace pf {
+template <int NF, int ND>
+__global__ void __launch_bounds__(256, 2) dfma_dmma_probe_kernel(double* out, int iters, double a, double b) {
+    double x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = a + i + threadIdx.x * 1e-3;
+        y[i] = 0.5 * b - i * 1e-9 - threadIdx.x * 1e-12;
+    }
+    double av = a * 1e-3 + threadIdx.x * 1e-9;
+    const double bv = b * 1e-3;
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        double c0[ND > 0 ? ND : 1], c1[ND > 0 ? ND : 1];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+                         : "=d"(c0[d]), "=d"(c1[d])
+                         : "d"(av), "d"(bv + d), "d"(0.0));
+        }
+#pragma unroll
+        for (int u = 0; u < NF; ++u) x[u & 7] = fma(x[u & 7], y[u & 7], 1.5);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc += c0[d] * 1e-30 + c1[d] * 1e-30;  // 2 more DFMAs per DMMA consume the tile
+        av += 1e-12;
+    }
+    double s = acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 12345.678) out[0] = s;
+}
+template <int NF, int ND>
+static float run_dfma_dmma_probe(int sms, int iters, double* d_out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dfma_dmma_probe_kernel<NF, ND><<<sms * 2, 256>>>(d_out, 16, 1.0000001, 0.9999999);
+    cudaEventRecord(e0);
+    dfma_dmma_probe_kernel<NF, ND><<<sms * 2, 256>>>(d_out, iters, 1.0000001, 0.9999999);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+}  // namespace pf
+
+// out8[i] = SM clocks (at 1.965 GHz) per block per SM sub-partition (4 warps each) for the (NF, ND) list above
+extern "C" PF_API int pf_debug_dfma_dmma_probe(int device, double* out8) {
+    if (!out8 || cudaSetDevice(device) != cudaSuccess) return PF_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PF_ERR_CUDA;
+    const int sms = prop.multiProcessorCount, iters = 20000;
+    double* d_out = nullptr;
+    if (cudaMalloc(&d_out, 64) != cudaSuccess) return PF_ERR_NOMEM;
+    const float ms[8] = {pf::run_dfma_dmma_probe<16, 0>(sms, iters, d_out), pf::run_dfma_dmma_probe<0, 2>(sms, iters, d_out),
+                         pf::run_dfma_dmma_probe<0, 4>(sms, iters, d_out),  pf::run_dfma_dmma_probe<16, 1>(sms, iters, d_out),
+                         pf::run_dfma_dmma_probe<16, 2>(sms, iters, d_out), pf::run_dfma_dmma_probe<16, 4>(sms, iters, d_out),
+                         pf::run_dfma_dmma_probe<32, 4>(sms, iters, d_out), pf::run_dfma_dmma_probe<8, 4>(sms, iters, d_out)};
+    // 16 warps per SM = 4 per sub-partition: clocks per block per warp = time * f / iters / 4
+    for (int i = 0; i < 8; ++i) out8[i] = (double) ms[i] * 1e-3 * 1.965e9 / iters / 4.0;
+    cudaFree(d_out);
+    return cudaGetLastError() == cudaSuccess ? PF_OK : PF_ERR_CUDA;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host-buffer call floor: one kernel launch whose last thread delivers a self-validating word to mapped pinned
 // memory, polled by the host -- the skeleton of pf_eval_frontier without any scoring.  Measured for a small and a

@@ -321,6 +321,9 @@ PF_API int pf_debug_issue_probe(int device, double* out4);
 /* Diagnostics: DFMA rate (1e12/s) with 1, 2, 3 distinct register operands per DFMA, then a
  * 2-register DFMA with 2 and 4 one-register ALU instructions between (register-file bandwidth); 5 values. */
 PF_API int pf_debug_rf_probe(int device, double* out5);
+/* Diagnostics: do DFMA (FP64 pipe) and DMMA m8n8k4 (tensor pipe) overlap?  SM clocks per block per sub-partition for
+ * blocks of (DFMAs, DMMAs) = (16,0) (0,2) (0,4) (16,1) (16,2) (16,4) (32,4) (8,4), every DMMA tile consumed by 2 DFMAs. */
+PF_API int pf_debug_dfma_dmma_probe(int device, double* out8);
 
 /* Diagnostics: the floor of a host-buffer call -- microseconds per {kernel launch, one word delivered to mapped host
  * memory, host polls it} for {24-byte parameters, 1 CTA}, {3.6 KB parameters, 1 CTA}, {24 B, 2 x SMs CTAs + ticket},

@@ -22,3 +22,8 @@ out8 = np.zeros(8)
 _lib.check(lib.pf_debug_dmma_probe(0, out8.ctypes.data_as(C.POINTER(C.c_double))), "dmma probe")
 print("DMMA m8n8k4 FMA/clk/SM; rows: warps/SM 8,16; cols: accumulator tiles per warp 1,2,4,8:")
 print(np.round(out8.reshape(2, 4) * 1e12 / clk / sms, 2))
+
+out8 = np.zeros(8)
+_lib.check(lib.pf_debug_dfma_dmma_probe(0, out8.ctypes.data_as(C.POINTER(C.c_double))), "dfma+dmma probe")
+print("clocks per block per sub-partition warp, (DFMA, DMMA) = (16,0) (0,2) (0,4) (16,1) (16,2) (16,4) (32,4) (8,4):")
+print(np.round(out8, 1))
