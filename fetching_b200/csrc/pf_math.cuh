@@ -602,6 +602,21 @@ __device__ __forceinline__ void mix_exp_accumulate_z(const double (&z)[G], doubl
     }
 }
 
+// R rows walking G / R components together: chain c belongs to row c % R
+template <int G, int R>
+__device__ __forceinline__ void mix_exp_accumulate_zr(const double (&z)[G], double (&lp)[R], unsigned tab_l) {
+    double g[G], tjs[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+        const double t = z[c] + kRintMagicRep;
+        g[c] = z[c] - (t - kRintMagicRep);
+        PF_MIX_EXP_CORE(t, tjs[c])
+    }
+    PF_MIX_EXP_POLY(G)
+#pragma unroll
+    for (int c = 0; c < G; ++c) lp[c % R] = fma(tjs[c], P[c], lp[c % R]);
+}
+
 // e = squared distance >= 0 (or NaN), clamped in place like mix_exp_accumulate: 7 FP64 + 5 other per component
 template <int G>
 __device__ __forceinline__ void mix_exp_accumulate_e(double (&e)[G], double& lp0, double& lp1, unsigned tab_l) {

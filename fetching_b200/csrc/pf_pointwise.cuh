@@ -26,7 +26,7 @@ namespace pf {
 //   rows per iteration 1                                                   6.67 / 0.989 / 26.0
 //   A_k and B_k both re-read (rows 2)                                      5.24 / 0.927 / 19.7
 #ifndef PF_MIX_RB
-#define PF_MIX_RB 2       // rows per iteration of the mixture loops
+#define PF_MIX_RB 4       // rows per iteration of the mixture loops
 #endif
 #ifndef PF_MIX_RELOAD
 #define PF_MIX_RELOAD 1   // factored form: 0 = theta-derived constants wherever the compiler puts them (registers),
@@ -223,14 +223,16 @@ struct MixtureModel {
     static constexpr bool HAS_REDO = !FACTORED;
     static constexpr bool HAS_FIXUP = BIG_EXP_TABLE;       // n ln 2 (and -|x|^2/2) added once per tile
     static constexpr int NCOMP = K;
-    static constexpr unsigned RB = BIG_EXP_TABLE ? PF_MIX_RB : 4;  // rows per loop iteration (FP32: MUFU-bound, 4 is best)
+    // rows per loop iteration (factored: PF_MIX_RB; clamped FP64 form: 2; FP32: MUFU-bound, 4 is best)
+    static constexpr unsigned RB = (FACT && BIG_EXP_TABLE) ? PF_MIX_RB : (BIG_EXP_TABLE ? 2 : 4);
     using Factored = MixtureModel<K, D, T, true>;           // the variant pw_frontier_body may switch to
     // doubles staged per node: theta as it is, or [K][D] B then [K] A
     static __host__ __device__ constexpr unsigned staged_len(unsigned theta_len) {
         return FACTORED ? theta_len + K : theta_len;
     }
     static constexpr bool PROD = FACTORED && (PF_MIX_PROD != 0);      // running product instead of a log per row
-    static constexpr bool PAIR = FACTORED && (PF_MIX_PAIR != 0) && RB == 2 && (K % 4 == 0) && (D % 2 == 0);
+    static constexpr bool PAIR = FACTORED && (PF_MIX_PAIR != 0) && (RB == 2 || RB == 4) && (K % 4 == 0) && (D % 2 == 0);
+    static constexpr bool QUAD = PAIR && RB == 4;
     struct RowState {
         unsigned redo;  // slow_path_accumulate() key, tested once per tile
         int nacc;       // sum of the rows' binary exponents (log_pos_acc / product form)
@@ -393,10 +395,60 @@ struct MixtureModel {
             mix_exp_accumulate_z<2 * G2, true>(z, lpa, lpb, nd.tab_s);  // even chains -> lpa, odd -> lpb
         }
     }
+    // four rows at once (RB = 4): 2 components x 4 rows in flight; every A_k / B_k operand serves four consecutive DFMAs
+    // MASKED (the uniform tail of a tile): rows whose bit in `valid` is clear arrive as x = 0 and count as a row sum of 1
+    template <bool MASKED = false>
+    static __device__ __forceinline__ double quad_fast(const Node& nd, const CT (&x)[4][D], RowState& st, unsigned valid = 15u) {
+        constexpr int R = 4, GC = 2;
+        double lp[R] = {0.0, 0.0, 0.0, 0.0};
+        const unsigned th_s = smem_u32(nd.th);
+#pragma unroll
+        for (int k0 = 0; k0 < K; k0 += GC) {
+            double z[R * GC], a[GC];
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[0]), "=d"(a[1]) : "r"(th_s + (unsigned) ((K * D + k0) * 8)));
+#pragma unroll
+            for (int g = 0; g < GC; ++g) {
+                double b[D];
+#pragma unroll
+                for (int j = 0; j < D; j += 2)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b[j]), "=d"(b[j + 1]) : "r"(th_s + (unsigned) (((k0 + g) * D + j) * 8)));
+#pragma unroll
+                for (int r = 0; r < R; ++r) z[R * g + r] = fma(b[0], x[r][0], a[g]);
+#pragma unroll
+                for (int j = 1; j < D; ++j)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) z[R * g + r] = fma(b[j], x[r][j], z[R * g + r]);
+            }
+            mix_exp_accumulate_zr<R * GC, R>(z, lp, nd.tab_s);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < D; ++j) st.xsq = fma(x[r][j], x[r][j], st.xsq);
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) lp[r] = ((valid >> r) & 1u) ? lp[r] : 1.0;
+        }
+        if constexpr (PROD) {
+            prod_accumulate(st, lp[0] * lp[1]);
+            prod_accumulate(st, lp[2] * lp[3]);
+            return 0.0;
+        } else {
+            double v = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v += log_pos_acc(lp[r], nd.ltab_s, st.nacc);
+            return v;
+        }
+    }
     // PAIR hot loop body: both rows' contributions go into the lane state (product form) or come back summed
-    static __device__ __forceinline__ double pair_fast(const Node& nd, const CT (&xa)[D], const CT (&xb)[D], RowState& st) {
+    template <bool MASKED = false>
+    static __device__ __forceinline__ double pair_fast(const Node& nd, const CT (&xa)[D], const CT (&xb)[D], RowState& st, unsigned valid = 3u) {
         double lpa, lpb;
         mix_sum2(nd, xa, xb, lpa, lpb);
+        if constexpr (MASKED) {
+            lpa = (valid & 1u) ? lpa : 1.0;
+            lpb = (valid & 2u) ? lpb : 1.0;
+        }
 #pragma unroll
         for (int j = 0; j < D; ++j) st.xsq = fma(xa[j], xa[j], st.xsq);
 #pragma unroll
@@ -573,10 +625,22 @@ struct PairRows<M, std::enable_if_t<M::PAIR>> { static constexpr bool value = tr
 template <class M>
 __host__ __device__ constexpr bool pair_rows() { return PairRows<M>::value; }
 
-template <class M, class Node, class X, class St>
-__device__ __forceinline__ double pair_call(const Node& nd, const X& xa, const X& xb, St& st) {
+template <class M, bool MASKED = false, class Node, class X, class St>
+__device__ __forceinline__ double pair_call(const Node& nd, const X& xa, const X& xb, St& st, unsigned valid = 3u) {
     if constexpr (pair_rows<M>())
-        return M::pair_fast(nd, xa, xb, st);
+        return M::template pair_fast<MASKED>(nd, xa, xb, st, valid);
+    else
+        return 0.0;
+}
+template <class M, class = void>
+struct QuadRows { static constexpr bool value = false; };
+template <class M>
+struct QuadRows<M, std::enable_if_t<M::QUAD>> { static constexpr bool value = true; };
+
+template <class M, bool MASKED = false, class Node, class X, class St>
+__device__ __forceinline__ double quad_call(const Node& nd, const X& x, St& st, unsigned valid = 15u) {
+    if constexpr (pair_rows<M>())
+        return M::template quad_fast<MASKED>(nd, x, st, valid);
     else
         return 0.0;
 }
@@ -789,7 +853,13 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
                 CT x[RB][DIM];
 #pragma unroll
                 for (unsigned u = 0; u < RB; ++u) load_row<T, DIM, CT>(base + (size_t) (j + u * nslots) * RB_BYTES, x[u]);
-                if constexpr (RB == 2 && pair_rows<M>()) {
+                if constexpr (RB == 4 && pair_rows<M>()) {
+#pragma unroll
+                    for (int n = 0; n < NPL; ++n) {
+                        const double v = quad_call<M>(nd[n], x, st[n]);
+                        if constexpr (!prod_rows<M>()) accS[n] += v;
+                    }
+                } else if constexpr (RB == 2 && pair_rows<M>()) {
 #pragma unroll
                     for (int n = 0; n < NPL; ++n) {
                         const double v = pair_call<M>(nd[n], x[0], x[1], st[n]);
@@ -811,7 +881,54 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
                 }
             }
         };
-        if constexpr (M::ITEM1)
+        if constexpr (pair_rows<M>() && NPL == 1) {
+            // UNIFORM row steps: every lane of the CTA runs the same number of iterations.  Full steps of RBm rows per
+            // slot first; what is left (< RBm * nslots rows) is one masked step in which the rows past the end arrive as
+            // x = 0 and count as a row sum of 1.  (With per-lane trip counts the warp holding the last slots ran an extra
+            // loop body per tile -- at B = 1, where a tile is four rows per lane, that warp bounded the CTA at +50 %.)
+            constexpr unsigned RBm = QuadRows<M>::value ? 4u : 2u;
+            unsigned left = nrows;
+            for (; left >= RBm * nslots; left -= RBm * nslots, j += RBm * nslots) {
+                CT x[RBm][DIM];
+#pragma unroll
+                for (unsigned u = 0; u < RBm; ++u) load_row<T, DIM, CT>(base + (size_t) (j + u * nslots) * RB_BYTES, x[u]);
+                double v;
+                if constexpr (RBm == 4)
+                    v = quad_call<M>(nd[0], x, st[0]);
+                else
+                    v = pair_call<M>(nd[0], x[0], x[1], st[0]);
+                if constexpr (!prod_rows<M>()) accS[0] += v;
+            }
+            auto masked_step = [&](auto rb_tag) {
+                constexpr unsigned RBt = decltype(rb_tag)::value;
+                CT x[RBt][DIM];
+                unsigned valid = 0u;
+#pragma unroll
+                for (unsigned u = 0; u < RBt; ++u) {
+                    const unsigned row = j + u * nslots;
+                    const bool ok = row < nrows;
+                    valid |= ok ? (1u << u) : 0u;
+                    load_row<T, DIM, CT>(base + (size_t) (ok ? row : 0u) * RB_BYTES, x[u]);
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) x[u][d] = ok ? x[u][d] : (CT) 0;
+                }
+                double v;
+                if constexpr (RBt == 4)
+                    v = quad_call<M, true>(nd[0], x, st[0], valid);
+                else
+                    v = pair_call<M, true>(nd[0], x[0], x[1], st[0], valid);
+                if constexpr (!prod_rows<M>()) accS[0] += v;
+                j += RBt * nslots;
+            };
+            if constexpr (RBm == 4) {
+                if (left > 2 * nslots)
+                    masked_step(std::integral_constant<unsigned, 4>{});
+                else if (left > 0)
+                    masked_step(std::integral_constant<unsigned, 2>{});
+            } else if (left > 0)
+                masked_step(std::integral_constant<unsigned, 2>{});
+            j = nrows;  // nothing left for the per-lane loops below
+        } else if constexpr (M::ITEM1)
             batch_rows(std::integral_constant<unsigned, 4>{});
         else if constexpr (NPL == 1) {
             if constexpr (M::RB >= 4)
