@@ -186,7 +186,7 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                                                unsigned long long row_end, unsigned long long rows_per_cta,
                                                unsigned long long item_rows, unsigned tid, unsigned B,
                                                double* scratch, int bar_id, unsigned nthreads, double& S_out,
-                                               double& Q_out) {
+                                               double& Q_out, double* big = nullptr, size_t big_doubles = 0) {
     unsigned gmax = grid;  // rows_per_cta == 0: every launched CTA wrote a plain (S, Q) record
     if (rows_per_cta) {
         const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
@@ -194,6 +194,17 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
     }
     const bool stitching = MAY_STITCH && item_rows > 1 && rows_per_cta;
     const unsigned nwarps = nthreads / 32, warp = tid / 32, lane = tid & 31;
+    // Items much longer than a CTA's row range (lasso: 18000-row items over ~700-row ranges) make every stitch a walk over
+    // the `head` partials of all the CTAs inside the item -- a chain of L2 round trips run by a single lane (25 CTAs per
+    // item at C4: the finalize took 0.8 us per node and stitch).  With shared memory to spare (`big`: the idle data ring
+    // of the matvec kernels) the heads are fetched once, coalesced, by all the threads, and the walks read shared memory.
+    const bool pre = stitching && big != nullptr && item_rows > 2 * rows_per_cta && (size_t) B * gmax <= big_doubles;
+    if (pre) {
+        for (unsigned b = warp; b < B; b += nwarps)
+            for (unsigned c = lane; c < gmax; c += 32) big[(size_t) b * gmax + c] = ld_cg_f64(part + (size_t) b * kMaxGrid +
+                                                                                               2 * (size_t) kMaxNodesPerPass * kMaxGrid + c);
+        named_bar_sync(bar_id, (int) nthreads);
+    }
     constexpr int BATCH = 10;
     constexpr size_t ROW = (size_t) kMaxGrid, SLOT = (size_t) kMaxNodesPerPass * kMaxGrid;
     for (unsigned b = warp; b < B; b += nwarps) {
@@ -231,7 +242,11 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                     if (st[u] >= 0.0) {
                         const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[u];
                         double tot = tl[u];
-                        for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS + 2 * SLOT + k);
+                        if (pre) {
+                            const double* const hb = big + (size_t) b * gmax;
+                            for (unsigned k = cs + 1; k < c; ++k) tot += hb[k];
+                        } else
+                            for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS + 2 * SLOT + k);
                         tot += hd[u];
                         S += tot;
                         Q = fma(tot, tot, Q);

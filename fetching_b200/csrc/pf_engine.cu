@@ -649,6 +649,14 @@ static void print_trace(Engine& e) {
             if (t[32 + 2 * c]) fprintf(stderr, " %.1f", (double) (long long) (t[33 + 2 * c] - t[0]) * 1e-3);
         fprintf(stderr, "\n");
     }
+#ifdef PF_TC_TIMELINE
+    if (t[400]) {
+        fprintf(stderr, "[pf timeline] step: tma-issued data-landed(split starts) mma-may-issue mma-issued (ns since CTA 0 entry)\n");
+        for (int q = 0; q < 200 && t[400 + q]; ++q)
+            fprintf(stderr, "[pf timeline] %3d: %7lld %7lld %7lld %7lld\n", q, (long long) (t[400 + q] - t[0]), (long long) (t[600 + q] - t[0]),
+                    (long long) (t[800 + q] - t[0]), (long long) (t[1000 + q] - t[0]));
+    }
+#endif
     memset(e.h_trace, 0, (32 + 2 * kMaxGrid) * sizeof(unsigned long long));
 }
 

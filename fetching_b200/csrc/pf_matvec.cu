@@ -459,8 +459,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
     {
         // Boltzmann: the records hold plain energy partials (one item): finalize with item_rows = 1
         double S, Q;
+        // (every load of this CTA has landed and been consumed: the X stages are scratch for the stitch walks)
         finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
-                       BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q);
+                       BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q, reinterpret_cast<double*>(smem),
+                       (size_t) MV_STAGES * MV_XSTAGE_BYTES / sizeof(double));
         trace_mark(a.trace, 1, 1, tid == 0);  // records folded
         unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {
@@ -673,7 +675,7 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     // (n = 1e5, p = 1000; ms per call, tcgen05 / CUDA cores): B = 8 0.167 / 0.094, 16 0.176 / 0.118, 32 0.197 / 0.184,
     // 64 0.244 / 0.351 -- the tensor path pays a fixed ~0.15 ms (X_lo pass + panel re-read per 128-row tile) and wins
     // once the CUDA cores are FMA-bound: it is the default above 32 nodes, and for any B with PF_OPT_MATVEC_TENSOR = 2.
-    if (e.f32 && !boltz && e.mv_tensor && (B > 32 || e.mv_tensor_force)) return launch_matvec_tc32(e, a, d_theta, s);
+    if (e.f32 && !boltz && e.mv_tensor && (B > 16 || e.mv_tensor_force)) return launch_matvec_tc32(e, a, d_theta, s);
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
     static bool prep_configured[64] = {};
