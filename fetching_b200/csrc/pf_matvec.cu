@@ -675,7 +675,7 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     // (n = 1e5, p = 1000; ms per call, tcgen05 / CUDA cores): B = 8 0.167 / 0.094, 16 0.176 / 0.118, 32 0.197 / 0.184,
     // 64 0.244 / 0.351 -- the tensor path pays a fixed ~0.15 ms (X_lo pass + panel re-read per 128-row tile) and wins
     // once the CUDA cores are FMA-bound: it is the default above 32 nodes, and for any B with PF_OPT_MATVEC_TENSOR = 2.
-    if (e.f32 && !boltz && e.mv_tensor && (B > 16 || e.mv_tensor_force)) return launch_matvec_tc32(e, a, d_theta, s);
+    if (e.f32 && !boltz && e.mv_tensor) return launch_matvec_tc32(e, a, d_theta, s);  // (faster than the CUDA cores at every B)
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;
     static bool prep_configured[64] = {};

@@ -69,6 +69,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp, chosen by the hardware: inside `if (elect_one())` ptxas knows that a single thread runs,
+// so uniform operands reach the tensor-core / TMA instructions straight from uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1), version 1
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     uint64_t d = (uint64_t) ((saddr & 0x3FFFFu) >> 4);
@@ -257,9 +267,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 4) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0 && r0 < r1) {
-            prefetch_tensormap(&a.tmap);
+        // ------------------------------------------------------------------ producer (whole warp walks, elected lane issues)
+        if (r0 < r1) {
+            if (elect_one()) prefetch_tensormap(&a.tmap);
             asm volatile("griddepcontrol.wait;" ::: "memory");  // the panel (prep kernel) is first touched below
             unsigned q = 0, pc = 0, s = 0, sph = 1;  // s = q % NS, sph = parity of q / NS - 1 (no division per step)
             unsigned long long g1;
@@ -268,19 +278,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
                 for (unsigned c = 0; c < n_chunks; ++c, ++pc) {
                     const unsigned ps = pc % TC_P_STAGES;
                     if (pc >= TC_P_STAGES) mbar_wait(&pempty[ps], ((pc / TC_P_STAGES) - 1) & 1);
-                    mbar_arrive_expect_tx(&pfull[ps], 2 * pbytes);  // beta_hi | beta_lo of this chunk are adjacent: one copy
-                    bulk_g2s(p_ring + (size_t) ps * 2 * pbytes, static_cast<const unsigned char*>(a.betaT) + (size_t) c * 2 * pbytes,
-                             2 * pbytes, &pfull[ps]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&pfull[ps], 2 * pbytes);  // beta_hi | beta_lo of this chunk are adjacent: one copy
+                        bulk_g2s(p_ring + (size_t) ps * 2 * pbytes, static_cast<const unsigned char*>(a.betaT) + (size_t) c * 2 * pbytes,
+                                 2 * pbytes, &pfull[ps]);
+                    }
+                    __syncwarp();
                     unsigned long long t0 = g0, t1;
                     for (unsigned i = 0; i < nt; ++i, ++q, t0 = t1) {
                         next_tile(t0, t1);
                         if (q >= NS) mbar_wait(&empty[s], sph);
-                        TC_TL(0, q);
                         unsigned char* st = x_ring + (size_t) s * TC_XBYTES;
                         const bool two = t1 - t0 > (unsigned long long) TC_BOX_ROWS;
-                        mbar_arrive_expect_tx(&full[s], two ? TC_XBYTES : TC_XBYTES / 2);
-                        tma_load_2d(st, &a.tmap, (int) (c * TC_KCH), (int) t0, &full[s]);
-                        if (two) tma_load_2d(st + TC_XBYTES / 2, &a.tmap, (int) (c * TC_KCH), (int) t0 + TC_BOX_ROWS, &full[s]);
+                        if (elect_one()) {
+                            TC_TL(0, q);
+                            mbar_arrive_expect_tx(&full[s], two ? TC_XBYTES : TC_XBYTES / 2);
+                            tma_load_2d(st, &a.tmap, (int) (c * TC_KCH), (int) t0, &full[s]);
+                            if (two) tma_load_2d(st + TC_XBYTES / 2, &a.tmap, (int) (c * TC_KCH), (int) t0 + TC_BOX_ROWS, &full[s]);
+                        }
+                        __syncwarp();
                         if (++s == NS) {
                             s = 0;
                             sph ^= 1u;
@@ -291,10 +307,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
         }
         __syncwarp();
     } else if (warp == 5) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && r0 < r1) {
+        // ------------------------------------------------------------------ MMA issuer: the WHOLE warp walks the loop
+        // (uniform control flow, operands in uniform registers) and an elected lane issues.  With the loop inside `if (lane == 0)`
+        // every descriptor reached the tensor-core instructions through a per-thread-to-uniform conversion loop
+        // (ELECT / R2UR.BROADCAST / BRA.U.ANY) and the issuing thread, not the tensor core, bounded the step.
+        if (r0 < r1) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = Npad, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((Npad >> 3) << 17) | ((TC_ROWS >> 4) << 24);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_acc, 0);
             unsigned q = 0, pc = 0, grp = 0;
             unsigned long long g1;
             for (unsigned long long g0 = r0; g0 < r1; g0 = g1, ++grp) {
@@ -310,21 +330,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
                         const unsigned at = q % TC_A_STAGES;
                         mbar_wait(&a_ready[at], (q / TC_A_STAGES) & 1);  // X_hi | X_lo of this step are in TMEM
                         tc_fence_after();
-                        TC_TL(2, q);
-                        const uint32_t a_hi = tmem_acc + TC_A_BASE + at * TC_A_COLS, a_lo = a_hi + TC_KCH;
-                        const uint32_t acc = tmem_acc + i * Npad;
+                        const uint32_t a_hi = tbase + TC_A_BASE + at * TC_A_COLS, a_lo = a_hi + TC_KCH;
+                        const uint32_t acc = tbase + i * Npad;
+                        if (elect_one()) {
+                            TC_TL(2, q);
 #pragma unroll
-                        for (unsigned k = 0; k < 4; ++k) {  // 8 floats per k-step: 8 TMEM columns of A, 2 descriptor units of B
-                            umma_tf32_ts(acc, a_hi + 8 * k, b_hi + 2 * k, idesc, (c | k) != 0);
-                            umma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, idesc, 1u);
-                            umma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+                            for (unsigned k = 0; k < 4; ++k) {  // 8 floats per k-step: 8 TMEM columns of A, 2 descriptor units of B
+                                umma_tf32_ts(acc, a_hi + 8 * k, b_hi + 2 * k, idesc, (c | k) != 0);
+                                umma_tf32_ts(acc, a_lo + 8 * k, b_hi + 2 * k, idesc, 1u);
+                                umma_tf32_ts(acc, a_hi + 8 * k, b_lo + 2 * k, idesc, 1u);
+                            }
+                            umma_commit(&a_free[at]);  // the A stage may be rewritten once these MMAs have read it
+                            TC_TL(3, q);
                         }
-                        umma_commit(&a_free[at]);  // the A stage may be rewritten once these MMAs have read it
-                        TC_TL(3, q);
+                        __syncwarp();
                     }
-                    umma_commit(&pempty[ps]);       // ... and the panel stage
+                    if (elect_one()) umma_commit(&pempty[ps]);  // ... and the panel stage
+                    __syncwarp();
                 }
-                umma_commit(acc_full);
+                if (elect_one()) umma_commit(acc_full);
+                __syncwarp();
             }
         }
         __syncwarp();

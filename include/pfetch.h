@@ -280,7 +280,7 @@ enum pf_option {
      * FP64: mma.sync.m8n8k4.f64 (DMMA) -- same IEEE arithmetic, different summation order over the columns.
      * PF_F32 lasso: tcgen05.mma kind::tf32 with every operand split into two tf32 pieces (hi.hi + lo.hi + hi.lo,
      * FP32 accumulation in TMEM): FP32-faithful to ~1e-6 relative, inside the 1e-5 contract of PF_F32; used for
-     * frontiers of more than 16 nodes (where it is faster than the CUDA cores), or for every size with value 2. */
+     * every frontier size (it is faster than the CUDA-core variant from B = 1 on); 0 selects the CUDA cores. */
     PF_OPT_MATVEC_TENSOR = 4,
     /* Host-pointer calls of the pointwise models: 1 (default) = frontiers of up to 432 doubles of theta travel in
      * the kernel parameters, 0 = always through a host->device copy in front of the kernel. */
