@@ -73,6 +73,34 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
+// L2 eviction policies for streamed data: a matrix that is read once per call and is larger than L2 (lasso: 400 / 800 MB
+// through 126 MB) otherwise pushes out everything the call still needs from L2 -- the coefficient panel every CTA
+// re-reads, and the per-CTA records the finalizing CTA folds (which then came back from HBM: 1.3 us per round trip).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -87,6 +115,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
+    const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), delta);
+    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), delta);
+    return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_xor_sync(0xffffffffu, lo, mask);
@@ -181,12 +214,22 @@ struct ItemOwner {
 // small call is the latency of these rounds (and, with one 8-byte request per thread, was their number: 7 us at B = 1).
 // `nthreads` consumer threads take part (tid < nthreads, whole warps); `scratch` holds 2 * kMaxNodesPerPass doubles.
 // Returns S/Q to threads tid < B.
-template <bool MAY_STITCH = true>
+// BATCH x 32 = CTAs folded per round (10: the 2 x 148 CTAs of the pointwise kernels in one round); NI = nodes a warp folds
+// TOGETHER (their loads in flight at the same time: the fold of a node is two or three dependent L2 / shared-memory
+// round trips, and at B = 64 a warp of the matvec kernels has eight nodes to fold -- <true, 5, 4> there).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <bool MAY_STITCH = true, int BATCH = 10, int NI = 1>
 __device__ __forceinline__ void finalize_items(const double* part, unsigned grid, unsigned long long row_begin,
                                                unsigned long long row_end, unsigned long long rows_per_cta,
                                                unsigned long long item_rows, unsigned tid, unsigned B,
                                                double* scratch, int bar_id, unsigned nthreads, double& S_out,
-                                               double& Q_out, double* big = nullptr, size_t big_doubles = 0) {
+                                               double& Q_out, double* big = nullptr, size_t big_doubles = 0,
+                                               unsigned long long* tr = nullptr) {
     unsigned gmax = grid;  // rows_per_cta == 0: every launched CTA wrote a plain (S, Q) record
     if (rows_per_cta) {
         const unsigned long long n_cta = (row_end - row_begin + rows_per_cta - 1) / rows_per_cta;
@@ -196,73 +239,145 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
     const unsigned nwarps = nthreads / 32, warp = tid / 32, lane = tid & 31;
     // Items much longer than a CTA's row range (lasso: 18000-row items over ~700-row ranges) make every stitch a walk over
     // the `head` partials of all the CTAs inside the item -- a chain of L2 round trips run by a single lane (25 CTAs per
-    // item at C4: the finalize took 0.8 us per node and stitch).  With shared memory to spare (`big`: the idle data ring
-    // of the matvec kernels) the heads are fetched once, coalesced, by all the threads, and the walks read shared memory.
-    const bool pre = stitching && big != nullptr && item_rows > 2 * rows_per_cta && (size_t) B * gmax <= big_doubles;
+    // item at C4).  With shared memory to spare (`big`: the idle data ring of the matvec kernels) the heads (and tails) are
+    // fetched once, coalesced, by all the threads, and turned into prefix sums (below).
+    constexpr unsigned PITCH = 32 * BATCH;  // row pitch of the staged partials (a compile-time divisor)
+    const bool pre = stitching && big != nullptr && item_rows > 2 * rows_per_cta && gmax <= PITCH && (size_t) B * PITCH <= big_doubles;
+    const bool pre_tail = pre && 2 * (size_t) B * PITCH <= big_doubles;  // ... and the tails, when there is room
     if (pre) {
-        for (unsigned b = warp; b < B; b += nwarps)
-            for (unsigned c = lane; c < gmax; c += 32) big[(size_t) b * gmax + c] = ld_cg_f64(part + (size_t) b * kMaxGrid +
-                                                                                               2 * (size_t) kMaxNodesPerPass * kMaxGrid + c);
+        // flat index space [heads | tails][node][PITCH], eight loads per thread in flight (a load-store loop would be one
+        // L2 round trip per iteration: 40 of them per warp at B = 64)
+        const unsigned per = B * PITCH, total = pre_tail ? 2 * per : per;
+        for (unsigned base = tid; base < total; base += nthreads * 8) {
+            double h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned idx = base + (unsigned) u * nthreads;
+                const unsigned slot = idx >= per ? 3u : 2u, r = idx >= per ? idx - per : idx;
+                const unsigned b = r / PITCH, c = r % PITCH;
+                h[u] = (idx < total && c < gmax)
+                           ? ld_cg_f64(part + (size_t) b * kMaxGrid + (size_t) slot * kMaxNodesPerPass * kMaxGrid + c)
+                           : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned idx = base + (unsigned) u * nthreads;
+                if (idx < total) big[idx] = h[u];
+            }
+        }
         named_bar_sync(bar_id, (int) nthreads);
     }
-    constexpr int BATCH = 10;
+    if (tr != nullptr && tid == 0) tr[16 + 3] = globaltimer_ns();  // diagnostics: heads / tails staged
     constexpr size_t ROW = (size_t) kMaxGrid, SLOT = (size_t) kMaxNodesPerPass * kMaxGrid;
-    for (unsigned b = warp; b < B; b += nwarps) {
-        const double* const pS = part + (size_t) b * ROW;
-        double S = 0.0, Q = 0.0;
+    for (unsigned b0 = warp * NI; b0 < B; b0 += nwarps * NI) {
+        const double* pS[NI];
+        bool on[NI];  // (uniform per warp) node b0 + i exists
+        double S[NI], Q[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            on[i] = b0 + i < B;
+            pS[i] = part + (size_t) (on[i] ? b0 + i : b0) * ROW;
+            S[i] = Q[i] = 0.0;
+        }
+        if (pre) {
+            // a node's heads -> INCLUSIVE PREFIX SUMS over the CTAs, in place (the warp that folds the node owns its row):
+            // a cut item's middle is then  P[c] - P[cs]  instead of a walk over the CTAs in between.  The difference of
+            // two prefixes carries an error of ~1e-16 of the node's total.
+            const unsigned per = (gmax + 31) / 32, k0 = lane * per;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if (!on[i]) continue;
+                double* const hb = big + (size_t) (b0 + i) * PITCH;
+                double run = 0.0;
+                for (unsigned k = k0; k < k0 + per && k < gmax; ++k) run += hb[k];
+                double incl = run;
+                for (int m = 1; m < 32; m <<= 1) {
+                    const double up = shfl_up_f64(incl, m);
+                    if ((int) lane >= m) incl += up;
+                }
+                double acc = incl - run;  // exclusive offset of this lane's chunk
+                for (unsigned k = k0; k < k0 + per && k < gmax; ++k) {
+                    acc += hb[k];
+                    hb[k] = acc;
+                }
+            }
+            __syncwarp();
+        }
         for (unsigned c0 = 0; c0 < gmax; c0 += 32 * BATCH) {
-            double s[BATCH], q[BATCH], st[BATCH];
+            double s[NI][BATCH], q[NI][BATCH], st[NI][BATCH];
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const unsigned c = c0 + u * 32 + lane;
-                const bool live = c < gmax;
-                s[u] = live ? ld_cg_f64(pS + c) : 0.0;
-                q[u] = live ? ld_cg_f64(pS + SLOT + c) : 0.0;
-                st[u] = (stitching && live) ? ld_cg_f64(pS + 4 * SLOT + c) : -1.0;
-            }
+            for (int i = 0; i < NI; ++i)
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                S += s[u];
-                Q += q[u];
-            }
+                for (int u = 0; u < BATCH; ++u) {
+                    const unsigned c = c0 + u * 32 + lane;
+                    const bool live = on[i] && c < gmax;
+                    s[i][u] = live ? ld_cg_f64(pS[i] + c) : 0.0;
+                    q[i][u] = live ? ld_cg_f64(pS[i] + SLOT + c) : 0.0;
+                    st[i][u] = (stitching && live) ? ld_cg_f64(pS[i] + 4 * SLOT + c) : -1.0;
+                }
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    S[i] += s[i][u];
+                    Q[i] += q[i][u];
+                }
             if (stitching) {
                 // a cut item ends in CTA c when st >= 0: its total is tail(cs) + head(cs + 1) + ... + head(c).  The two
                 // loads every stitch needs are issued for the whole round before any use; CTAs in between exist only
                 // when an item spans more than two CTAs.
-                double tl[BATCH], hd[BATCH];
+                double tl[NI][BATCH], hd[NI][BATCH];
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) {
-                    const bool stitch = st[u] >= 0.0;
-                    const unsigned c = c0 + u * 32 + lane, cs = stitch ? (unsigned) st[u] : 0u;
-                    tl[u] = stitch ? ld_cg_f64(pS + 3 * SLOT + cs) : 0.0;
-                    hd[u] = stitch ? ld_cg_f64(pS + 2 * SLOT + c) : 0.0;
-                }
+                for (int i = 0; i < NI; ++i)
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) {
-                    if (st[u] >= 0.0) {
-                        const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[u];
-                        double tot = tl[u];
-                        if (pre) {
-                            const double* const hb = big + (size_t) b * gmax;
-                            for (unsigned k = cs + 1; k < c; ++k) tot += hb[k];
-                        } else
-                            for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS + 2 * SLOT + k);
-                        tot += hd[u];
-                        S += tot;
-                        Q = fma(tot, tot, Q);
+                    for (int u = 0; u < BATCH; ++u) {
+                        const bool stitch = st[i][u] >= 0.0;
+                        const unsigned c = c0 + u * 32 + lane, cs = stitch ? (unsigned) st[i][u] : 0u;
+                        if (pre_tail) {
+                            tl[i][u] = stitch ? big[(size_t) (B + b0 + i) * PITCH + cs] : 0.0;
+                            hd[i][u] = 0.0;
+                        } else {
+                            tl[i][u] = stitch ? ld_cg_f64(pS[i] + 3 * SLOT + cs) : 0.0;
+                            hd[i][u] = (stitch && !pre) ? ld_cg_f64(pS[i] + 2 * SLOT + c) : 0.0;
+                        }
                     }
-                }
+#pragma unroll
+                for (int i = 0; i < NI; ++i)
+#pragma unroll
+                    for (int u = 0; u < BATCH; ++u) {
+                        if (st[i][u] >= 0.0) {
+                            const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[i][u];
+                            double tot = tl[i][u];
+                            if (pre) {
+                                const double* const hb = big + (size_t) (b0 + i) * PITCH;
+                                tot += hb[c] - hb[cs];  // heads of the CTAs cs + 1 .. c
+                            } else {
+                                for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS[i] + 2 * SLOT + k);
+                                tot += hd[i][u];
+                            }
+                            S[i] += tot;
+                            Q[i] = fma(tot, tot, Q[i]);
+                        }
+                    }
             }
         }
-        for (int m = 16; m >= 1; m >>= 1) {
-            S += shfl_xor_f64(S, m);
-            Q += shfl_xor_f64(Q, m);
-        }
+        for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                S[i] += shfl_xor_f64(S[i], m);
+                Q[i] += shfl_xor_f64(Q[i], m);
+            }
         if (lane == 0) {
-            scratch[b] = S;
-            scratch[kMaxNodesPerPass + b] = Q;
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+                if (on[i]) {
+                    scratch[b0 + i] = S[i];
+                    scratch[kMaxNodesPerPass + b0 + i] = Q[i];
+                }
         }
+        if (tr != nullptr && tid == 0 && b0 == 0) tr[16 + 4] = globaltimer_ns();  // first round of warp 0
     }
+    if (tr != nullptr && tid == 0) tr[16 + 5] = globaltimer_ns();  // warp 0 done
     named_bar_sync(bar_id, (int) nthreads);
     double S = 0.0, Q = 0.0;
     if (tid < B) {
@@ -287,11 +402,6 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
 // A peer that never shows up (died, or made a different sequence of calls) trips a 20 s timeout:
 // *status = 1 in mapped host memory and the caller reports an error instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // Result delivery of the host path: value i of n as two self-validating 8-byte words (see PointwiseArgs::done_flag).
 __device__ __forceinline__ void store_result_words(double* out, unsigned i, double v, unsigned long long seq) {

@@ -188,14 +188,21 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
             UnitIter<BOLTZ> it = proto;
             unsigned long long t0, t1;
             unsigned c0, c1, q = 0;
+            [[maybe_unused]] const uint64_t pol_x = l2_policy_evict_first(), pol_p = l2_policy_evict_last();
             while (it.next(t0, t1, c0, c1)) {
                 for (unsigned c = c0; c < c1; ++c, ++q) {
                     const unsigned s = q % MV_STAGES;
                     if (q >= MV_STAGES) mbar_wait(&empty[s], ((q / MV_STAGES) - 1) & 1);
                     mbar_arrive_expect_tx(&full[s], xbytes + bbytes);
-                    tma_load_2d(xstage + s * MV_XSTAGE_BYTES, &a.tmap, (int) (c * KCH), (int) t0, &full[s]);
-                    bulk_g2s(bstage + s * MV_BSTAGE_BYTES,
-                             static_cast<const unsigned char*>(a.betaT) + (size_t) c * bbytes, bbytes, &full[s]);
+                    if constexpr (BOLTZ) {  // W (8 MB) stays in L2 between calls: default policy
+                        tma_load_2d(xstage + s * MV_XSTAGE_BYTES, &a.tmap, (int) (c * KCH), (int) t0, &full[s]);
+                        bulk_g2s(bstage + s * MV_BSTAGE_BYTES,
+                                 static_cast<const unsigned char*>(a.betaT) + (size_t) c * bbytes, bbytes, &full[s]);
+                    } else {  // the matrix streams through L2 once per call; the panel and the CTA records must survive it
+                        tma_load_2d_hint(xstage + s * MV_XSTAGE_BYTES, &a.tmap, (int) (c * KCH), (int) t0, &full[s], pol_x);
+                        bulk_g2s_hint(bstage + s * MV_BSTAGE_BYTES,
+                                      static_cast<const unsigned char*>(a.betaT) + (size_t) c * bbytes, bbytes, &full[s], pol_p);
+                    }
                 }
             }
         }
@@ -460,9 +467,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) mv_frontier_kernel(const __grid
         // Boltzmann: the records hold plain energy partials (one item): finalize with item_rows = 1
         double S, Q;
         // (every load of this CTA has landed and been consumed: the X stages are scratch for the stitch walks)
-        finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
-                       BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q, reinterpret_cast<double*>(smem),
-                       (size_t) MV_STAGES * MV_XSTAGE_BYTES / sizeof(double));
+        if (gridDim.x <= 160 && B > 2 * MV_CONSUMER_WARPS)  // more than two nodes per warp: four at a time
+            finalize_items<true, 5, 4>(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
+                                       BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q, reinterpret_cast<double*>(smem),
+                                       (size_t) MV_STAGES * MV_XSTAGE_BYTES / sizeof(double));
+        else
+            finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, BOLTZ ? 0ull : a.rows_per_cta,
+                           BOLTZ ? 1ull : a.item_rows, tid, B, red, 1, MV_CONSUMERS, S, Q, reinterpret_cast<double*>(smem),
+                           (size_t) MV_STAGES * MV_XSTAGE_BYTES / sizeof(double));
         trace_mark(a.trace, 1, 1, tid == 0);  // records folded
         unsigned Bout = B;  // node split: the gathered frontier is wider than this rank's slice
         if (a.xchg.nranks > 1) {

@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
             if (elect_one()) prefetch_tensormap(&a.tmap);
             asm volatile("griddepcontrol.wait;" ::: "memory");  // the panel (prep kernel) is first touched below
             unsigned q = 0, pc = 0, s = 0, sph = 1;  // s = q % NS, sph = parity of q / NS - 1 (no division per step)
+            const uint64_t pol_x = l2_policy_evict_first(), pol_p = l2_policy_evict_last();  // X streams, the panel is re-read
             unsigned long long g1;
             for (unsigned long long g0 = r0; g0 < r1; g0 = g1) {
                 const unsigned nt = group_tiles(g0, g1);
@@ -280,8 +281,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
                     if (pc >= TC_P_STAGES) mbar_wait(&pempty[ps], ((pc / TC_P_STAGES) - 1) & 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&pfull[ps], 2 * pbytes);  // beta_hi | beta_lo of this chunk are adjacent: one copy
-                        bulk_g2s(p_ring + (size_t) ps * 2 * pbytes, static_cast<const unsigned char*>(a.betaT) + (size_t) c * 2 * pbytes,
-                                 2 * pbytes, &pfull[ps]);
+                        bulk_g2s_hint(p_ring + (size_t) ps * 2 * pbytes,
+                                      static_cast<const unsigned char*>(a.betaT) + (size_t) c * 2 * pbytes, 2 * pbytes, &pfull[ps], pol_p);
                     }
                     __syncwarp();
                     unsigned long long t0 = g0, t1;
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
                         if (elect_one()) {
                             TC_TL(0, q);
                             mbar_arrive_expect_tx(&full[s], two ? TC_XBYTES : TC_XBYTES / 2);
-                            tma_load_2d(st, &a.tmap, (int) (c * TC_KCH), (int) t0, &full[s]);
-                            if (two) tma_load_2d(st + TC_XBYTES / 2, &a.tmap, (int) (c * TC_KCH), (int) t0 + TC_BOX_ROWS, &full[s]);
+                            tma_load_2d_hint(st, &a.tmap, (int) (c * TC_KCH), (int) t0, &full[s], pol_x);
+                            if (two)
+                                tma_load_2d_hint(st + TC_XBYTES / 2, &a.tmap, (int) (c * TC_KCH), (int) t0 + TC_BOX_ROWS, &full[s], pol_x);
                         }
                         __syncwarp();
                         if (++s == NS) {
@@ -477,8 +479,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mv_tc32_frontier_kernel(const _
             __threadfence();
             double S, Q;
             // every TMA load of this CTA has landed and been consumed: the X ring is scratch for the stitch walks
-            finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows, ftid, B, red, 2,
-                           TC_TEAMS * TC_WORKERS, S, Q, reinterpret_cast<double*>(x_ring), (size_t) NS * TC_XBYTES / sizeof(double));
+            if (gridDim.x <= 160 && B > 2 * TC_TEAMS * 4)  // (at most 148 CTAs here) more than two nodes per warp: four at a time
+                finalize_items<true, 5, 4>(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows, ftid, B, red, 2,
+                                           TC_TEAMS * TC_WORKERS, S, Q, reinterpret_cast<double*>(x_ring),
+                                           (size_t) NS * TC_XBYTES / sizeof(double), a.trace);
+            else
+                finalize_items(a.part, gridDim.x, a.row_begin, a.row_end, a.rows_per_cta, a.item_rows, ftid, B, red, 2,
+                               TC_TEAMS * TC_WORKERS, S, Q, reinterpret_cast<double*>(x_ring),
+                               (size_t) NS * TC_XBYTES / sizeof(double));
             trace_mark(a.trace, 1, 1, tid == 0);
             unsigned Bout = B;
             if (a.xchg.nranks > 1) {
