@@ -7,10 +7,13 @@ run() { echo "== $1 B=$2 ${3:-f64}" >> "$out"; timeout 600 python bench.py --no-
 for w in normal1e6 mixture1e6 blasso; do for b in 1 8 64; do run $w $b; done; done
 run blasso 16
 run blasso 32
+run blasso 1 f32
 run blasso 8 f32
+run blasso 32 f32
 run blasso 64 f32
 run boltzmann 64
 run mixture1e8 1
+run mixture1e8 16
 run mixture1e8 32
 run mixture1e8 64
 run mixture1e8 8 f32

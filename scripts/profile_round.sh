@@ -28,6 +28,7 @@ lasso)
   cap blasso_B8 mv_frontier --workload blasso
   cap blasso_B64 mv_frontier --workload blasso --frontier 64
   cap blasso_f32_B64_tcgen05 mv_tc32 --workload blasso --frontier 64 --dtype f32
+  cap blasso_f32_B8_tcgen05 mv_tc32 --workload blasso --frontier 8 --dtype f32
   ;;
 esac
 ls -la $o/r2_prof_*.ncu-rep $o/r2_launches_*.csv 2>/dev/null
