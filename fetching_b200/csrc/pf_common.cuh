@@ -417,7 +417,16 @@ __device__ __forceinline__ void trace_mark(unsigned long long* tr, int row, int 
 }
 // ... and per CTA: [32 + 2 * cta] = kernel entry, [33 + 2 * cta] = record published
 __device__ __forceinline__ void trace_cta(unsigned long long* tr, int which, bool who) {
+#ifdef PF_TRACE_SMID  // diagnostics: the low byte of the ENTRY time carries the SM the CTA runs on
+    if (tr != nullptr && who) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned long long t = globaltimer_ns();
+        tr[32 + 2 * blockIdx.x + which] = which == 0 ? ((t & ~0xFFull) | (smid & 0xFFu)) : t;
+    }
+#else
     if (tr != nullptr && who) tr[32 + 2 * blockIdx.x + which] = globaltimer_ns();
+#endif
 }
 
 static __device__ __noinline__ double2 peer_allreduce(const PeerXchg x, unsigned tid, unsigned B, unsigned nthreads,

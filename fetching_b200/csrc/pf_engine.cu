@@ -646,6 +646,12 @@ static void print_trace(Engine& e) {
                 in.size(), in.front(), in[in.size() / 2], in.back(), out.front(), out[out.size() / 2], out.back());
     }
     if (const char* tr = getenv("PF_TRACE"); tr && tr[0] == '1' && tr[1] == '1') {  // PF_TRACE=11: every CTA
+#ifdef PF_TRACE_SMID
+        fprintf(stderr, "[pf trace] SM of every CTA:");
+        for (int c = 0; c < kMaxGrid; ++c)
+            if (t[32 + 2 * c]) fprintf(stderr, " %u", (unsigned) (t[32 + 2 * c] & 0xFFull));
+        fprintf(stderr, "\n");
+#endif
         fprintf(stderr, "[pf trace] published(us) by CTA:");
         for (int c = 0; c < kMaxGrid; ++c)
             if (t[32 + 2 * c]) fprintf(stderr, " %.1f", (double) (long long) (t[33 + 2 * c] - t[0]) * 1e-3);
