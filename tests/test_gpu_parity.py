@@ -320,12 +320,15 @@ def test_blasso_tensor_variant_matches_vector_variant(fb, orc, n, p, item_rows, 
 
 @pytest.mark.parametrize("n,p,item_rows,B", [(6000, 100, 500, 16), (5000, 37, 333, 9), (20000, 16, 18000, 64),
                                               (777, 3, 100, 24), (4096, 1000, 1000, 40), (6000, 100, 500, 3),
-                                              (1000, 64, 50, 1), (30000, 257, 1000, 8)])
+                                              (1000, 64, 50, 1), (30000, 257, 1000, 8),
+                                              # more row tiles per CTA than TMEM has accumulators for: several groups
+                                              (200000, 33, 18000, 64), (150000, 8, 100, 64), (260000, 40, 7000, 40)])
 def test_blasso_f32_tcgen05_contraction_is_fp32_faithful(fb, orc, n, p, item_rows, B):
     """PF_F32 lasso: the contraction runs on the tcgen05 tensor cores as 3xTF32 (hi.hi + lo.hi + hi.lo, FP32 accumulate
     in TMEM).  Against the oracle on the float-rounded data the error must look like FP32 arithmetic, not like tf32
     (2^-10): well inside the 1e-5 contract; and it must agree with the CUDA-core FP32 variant to the same level.
-    Shapes cover items shorter than a 128-row tile, items straddling tiles, p not a multiple of 32, every N padding."""
+    Shapes cover items shorter than a 128-row tile, items straddling tiles, p not a multiple of 32, every N padding, and
+    CTAs with more tiles than accumulator slots (the chunk loop then runs once per group of tiles)."""
     from fetching_b200 import models
     X, y, beta = models.blasso_dataset(n, p, seed=p)
     th = models.blasso_thetas(beta, B, seed=2, scale=0.02)
