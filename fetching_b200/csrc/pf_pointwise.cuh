@@ -989,7 +989,9 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
             for (int n = 0; n < NPL; ++n) {
                 double v = accS[n];
                 accS[n] = 0.0;
-                for (unsigned m = 16; m >= NB; m >>= 1) v += shfl_xor_f64(v, m);
+#pragma unroll
+                for (unsigned m = 16; m >= 1; m >>= 1)  // (unrolled: the run-time loop cost 10 instructions per step -- at B = 1,
+                    if (m >= NB) v += shfl_xor_f64(v, m);  //  five steps per four rows of a lane; NB is warp-uniform)
                 if (pl == 0) r[warp * RS + nb + 32 * n] = v;
             }
             const int bar = PW_BAR_TILE0 + (int) (tt & (PW_RED_BUFS - 1));
