@@ -645,6 +645,10 @@ int dispatch_mma(Engine& e, MatvecArgs& a, unsigned nbk, cudaStream_t s) {
         case 1: return launch_mv<double, 1, BOLTZ, 1, MB>(e, a, s);
         case 2: return launch_mv<double, 1, BOLTZ, 2, MB>(e, a, s);
         case 4: return launch_mv<double, 1, BOLTZ, 4, MB>(e, a, s);
+        case 3: if constexpr (!BOLTZ) return launch_mv<double, 1, BOLTZ, 3, MB>(e, a, s);
+        case 5: if constexpr (!BOLTZ) return launch_mv<double, 1, BOLTZ, 5, MB>(e, a, s);
+        case 6: if constexpr (!BOLTZ) return launch_mv<double, 1, BOLTZ, 6, MB>(e, a, s);
+        case 7: if constexpr (!BOLTZ) return launch_mv<double, 1, BOLTZ, 7, MB>(e, a, s);
         default: return launch_mv<double, 1, BOLTZ, 8, MB>(e, a, s);
     }
 }
@@ -659,6 +663,9 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     while (NG * MV_NODES_PER_LANE < B) NG *= 2;  // 1, 2, 4, 8
     const unsigned rpl = NG == 1 ? 1 : (NG == 2 ? 2 : 4);
     const bool mma = !e.f32 && e.mv_tensor;  // FP64: the contraction runs on the tensor cores (DMMA)
+    // lasso on the tensor cores: node blocks of 8 in ANY number up to 8 (the DMMA-bound frontiers cost what their padded
+    // width costs: B = 40 ran as 64 nodes); the CUDA-core layouts and the Boltzmann unit split keep powers of two
+    if (mma && !boltz) NG = (B + MV_NODES_PER_LANE - 1) / MV_NODES_PER_LANE;
     // short tiles for a Boltzmann matrix whose 64-row tiles do not outnumber the SMs (see mv_frontier_kernel)
     const bool short_tiles = mma && boltz && (e.n_rows + 63) / 64 <= (uint64_t) e.sm_count;
     a.tile_rows = mma ? (short_tiles ? 64 : 256) : (MV_CONSUMER_WARPS / NG) * 32 * rpl;  // vector: 256, 256, 256, 128

@@ -298,7 +298,8 @@ def test_blasso_shapes(fb, orc, n, p, item_rows):
 
 @pytest.mark.parametrize("n,p,item_rows,B", [(6000, 100, 500, 16), (5000, 37, 333, 9), (20000, 16, 18000, 64),
                                               (777, 3, 100, 24), (4096, 1000, 1000, 40), (6000, 100, 500, 3),
-                                              (10000, 250, 1000, 8)])
+                                              (10000, 250, 1000, 8), (9000, 130, 1000, 20), (7000, 64, 700, 47),
+                                              (36000, 96, 18000, 50)])  # (node blocks of 8: 3, 6 and 7 of them)
 def test_blasso_tensor_variant_matches_vector_variant(fb, orc, n, p, item_rows, B):
     """FP64 runs the contraction on the FP64 tensor cores (DMMA m8n8k4); PF_OPT_MATVEC_TENSOR = 0 selects the
     CUDA-core FMA variant.  Both are exact IEEE FP64 FMAs, only the summation order over columns differs."""
