@@ -691,9 +691,8 @@ int launch_matvec(Engine& e, uint32_t B, const double* d_theta, double* d_out, u
     if (a.row_end <= a.row_begin) return launch_exchange_only(e, B, d_out, s);  // no rows here: zeros (+ the exchange)
     a.xchg = e.next_xchg();
     // PF_F32 lasso: the contraction on the tcgen05 tensor cores, FP32-faithful (3xTF32, pf_matvec_tc.cu).  Measured at C4
-    // (n = 1e5, p = 1000; ms per call, tcgen05 / CUDA cores): B = 8 0.167 / 0.094, 16 0.176 / 0.118, 32 0.197 / 0.184,
-    // 64 0.244 / 0.351 -- the tensor path pays a fixed ~0.15 ms (X_lo pass + panel re-read per 128-row tile) and wins
-    // once the CUDA cores are FMA-bound: it is the default above 32 nodes, and for any B with PF_OPT_MATVEC_TENSOR = 2.
+    // (n = 1e5, p = 1000; ms per call, tcgen05 / CUDA cores): B = 1 0.080 / 0.089, 8 0.078 / 0.091, 16 0.083 / 0.118,
+    // 32 0.092 / 0.188, 64 0.122 / 0.361 -- the default for every B; PF_OPT_MATVEC_TENSOR = 0 selects the CUDA cores.
     if (e.f32 && !boltz && e.mv_tensor) return launch_matvec_tc32(e, a, d_theta, s);  // (faster than the CUDA cores at every B)
     const unsigned off = boltz ? 0 : 1;
     const unsigned total = e.cols_pad * a.Bpad;

@@ -8,19 +8,21 @@
 // sees in v, lo = v - hi rounded to tf32, and the product is formed as   hi.hi + lo.hi + hi.lo   with FP32
 // accumulation in TMEM ("3xTF32": ~2^-21 per operand instead of tf32's 2^-10; the lo.lo term is below 2^-20 of that).
 //
-// DESIGN (B200).  One CTA per SM, 192 threads:
-//   warp 4 lane 0   producer: per (128-row tile, 32-column chunk) one 2-D TMA box of X (128 x 128 B, SWIZZLE_128B --
-//                   exactly the canonical K-major UMMA operand layout) + the chunk's beta_hi / beta_lo panels (written
-//                   by the prep kernel in that same swizzled layout, so a plain bulk copy lands them ready to use);
-//   warps 0-3       split: X_lo = X - tf32(X) for the landed tile, element for element at the same shared-memory
-//                   offsets (the swizzle is a permutation of 16-byte vectors, an elementwise pass does not care),
-//                   conflict-free LDS.128 / STS.128, then fence.proxy.async so the tensor core's async proxy sees it;
-//   warp 5 lane 0   MMA issuer: per chunk 4 k-steps x {hi.hi, lo.hi, hi.lo} = 12 tcgen05.mma.kind::tf32
-//                   (M = 128, N = Npad, K = 8) into one FP32 accumulator tile in TMEM; tcgen05.commit frees the stage;
-//   warps 0-3       epilogue per tile: tcgen05.ld (32x32b: thread = row) -> residual, square, per-node constants in
-//                   FP64 -> item totals exactly like pf_matvec.cu (ItemOwner / finalize_items / peer exchange).
-// Shared memory: a deep ring of landed X boxes with their panels (8 stages at N = 16, 5 at N = 64: what keeps HBM busy)
-// and a 2-stage ring of X_lo tiles, which only live from the split to the completion of the MMAs that read them.
+// DESIGN (B200).  One CTA per SM, 320 threads (DESIGN.md section 4.3 has the measurements behind every choice):
+//   warp 4          TMA producer (whole warp walks, an elected lane issues): per step -- one 128-row tile x one 32-column
+//                   chunk -- two 2-D boxes of X (64 rows x 128 B each, SWIZZLE_128B, L2 evict_first) into a deep ring;
+//                   per chunk, ONCE for all tiles of the group, the beta_hi | beta_lo panel (written by the prep kernel in
+//                   the swizzled K-major UMMA layout, L2 evict_last);
+//   warps 0-3, 6-9  two split teams on alternate steps (one warp per TMEM lane quarter): thread = row reads the landed box
+//                   (8 x LDS.128 through the swizzle), releases the shared-memory stage, and stores X_hi (the raw words)
+//                   and X_lo = X - tf32(X) into the team's A stage in TENSOR MEMORY (tcgen05.st);
+//   warp 5          MMA issuer (whole warp walks, an elected lane issues): per step 4 k-steps x {hi.hi, lo.hi, hi.lo} = 12
+//                   tcgen05.mma.kind::tf32 with A from TMEM and B by shared-memory descriptor (M = 128, N = Npad, K = 8)
+//                   into the tile's own FP32 accumulator in TMEM -- (512 - 128) / Npad accumulators: the chunk loop runs
+//                   over all tiles of a group; tcgen05.commit frees the A stage / the panel stage / hands over the group;
+//   warps 0-3       epilogue per item segment: tcgen05.ld (thread = row) -> residual, square, per-node constants in FP64,
+//                   summed per thread over the segment's tiles, one transposed 16-value warp reduction -> item totals
+//                   exactly like pf_matvec.cu (ItemOwner / finalize_items / peer exchange; both teams run the finalize).
 #include <math.h>
 #include <stdio.h>
 
