@@ -245,13 +245,14 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
     const bool pre = stitching && big != nullptr && item_rows > 2 * rows_per_cta && gmax <= PITCH && (size_t) B * PITCH <= big_doubles;
     const bool pre_tail = pre && 2 * (size_t) B * PITCH <= big_doubles;  // ... and the tails, when there is room
     if (pre) {
-        // flat index space [heads | tails][node][PITCH], eight loads per thread in flight (a load-store loop would be one
+        // flat index space [heads | tails][node][PITCH], sixteen loads per thread in flight (a load-store loop would be one
         // L2 round trip per iteration: 40 of them per warp at B = 64)
         const unsigned per = B * PITCH, total = pre_tail ? 2 * per : per;
-        for (unsigned base = tid; base < total; base += nthreads * 8) {
-            double h[8];
+        constexpr int SU = 16;  // loads in flight per thread
+        for (unsigned base = tid; base < total; base += nthreads * SU) {
+            double h[SU];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < SU; ++u) {
                 const unsigned idx = base + (unsigned) u * nthreads;
                 const unsigned slot = idx >= per ? 3u : 2u, r = idx >= per ? idx - per : idx;
                 const unsigned b = r / PITCH, c = r % PITCH;
@@ -260,7 +261,7 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                            : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < SU; ++u) {
                 const unsigned idx = base + (unsigned) u * nthreads;
                 if (idx < total) big[idx] = h[u];
             }
@@ -284,25 +285,35 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
             // a cut item's middle is then  P[c] - P[cs]  instead of a walk over the CTAs in between.  The difference of
             // two prefixes carries an error of ~1e-16 of the node's total.
             const unsigned per = (gmax + 31) / 32, k0 = lane * per;
+            double* hb[NI];
+            double run[NI], acc[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                if (!on[i]) continue;
-                double* const hb = big + (size_t) (b0 + i) * PITCH;
-                double run = 0.0;
-                for (unsigned k = k0; k < k0 + per && k < gmax; ++k) run += hb[k];
-                double incl = run;
-                for (int m = 1; m < 32; m <<= 1) {
-                    const double up = shfl_up_f64(incl, m);
-                    if ((int) lane >= m) incl += up;
-                }
-                double acc = incl - run;  // exclusive offset of this lane's chunk
-                for (unsigned k = k0; k < k0 + per && k < gmax; ++k) {
-                    acc += hb[k];
-                    hb[k] = acc;
-                }
+                hb[i] = big + (size_t) (on[i] ? b0 + i : b0) * PITCH;  // (a missing node repeats node b0: same values rewritten)
+                run[i] = 0.0;
             }
+            for (unsigned k = k0; k < k0 + per && k < gmax; ++k)  // the NI nodes side by side: their chains overlap
+#pragma unroll
+                for (int i = 0; i < NI; ++i) run[i] += hb[i][k];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] = run[i];
+            for (int m = 1; m < 32; m <<= 1)
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const double up = shfl_up_f64(acc[i], m);
+                    if ((int) lane >= m) acc[i] += up;
+                }
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] -= run[i];  // exclusive offset of this lane's chunk
+            for (unsigned k = k0; k < k0 + per && k < gmax; ++k)
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    acc[i] += hb[i][k];
+                    if (on[i]) hb[i][k] = acc[i];
+                }
             __syncwarp();
         }
+        if (tr != nullptr && tid == 0 && b0 == 0) tr[16 + 6] = globaltimer_ns();  // diagnostics: prefix sums done
         for (unsigned c0 = 0; c0 < gmax; c0 += 32 * BATCH) {
             double s[NI][BATCH], q[NI][BATCH], st[NI][BATCH];
 #pragma unroll
@@ -322,6 +333,7 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                     S[i] += s[i][u];
                     Q[i] += q[i][u];
                 }
+            if (tr != nullptr && tid == 0 && b0 == 0) tr[16 + 7] = globaltimer_ns();  // records loaded and summed
             if (stitching) {
                 // a cut item ends in CTA c when st >= 0: its total is tail(cs) + head(cs + 1) + ... + head(c).  The two
                 // loads every stitch needs are issued for the whole round before any use; CTAs in between exist only
@@ -341,26 +353,45 @@ __device__ __forceinline__ void finalize_items(const double* part, unsigned grid
                             hd[i][u] = (stitch && !pre) ? ld_cg_f64(pS[i] + 2 * SLOT + c) : 0.0;
                         }
                     }
+                if (pre) {  // branch free: every shared-memory read of the round is issued before the first use
+                    double pc[NI][BATCH], ps[NI][BATCH];
 #pragma unroll
-                for (int i = 0; i < NI; ++i)
+                    for (int i = 0; i < NI; ++i)
 #pragma unroll
-                    for (int u = 0; u < BATCH; ++u) {
-                        if (st[i][u] >= 0.0) {
-                            const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[i][u];
-                            double tot = tl[i][u];
-                            if (pre) {
-                                const double* const hb = big + (size_t) (b0 + i) * PITCH;
-                                tot += hb[c] - hb[cs];  // heads of the CTAs cs + 1 .. c
-                            } else {
-                                for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS[i] + 2 * SLOT + k);
-                                tot += hd[i][u];
-                            }
+                        for (int u = 0; u < BATCH; ++u) {
+                            const bool stitch = st[i][u] >= 0.0;
+                            const unsigned c = c0 + u * 32 + lane;  // (< PITCH: inside the node's staged row)
+                            const unsigned cs = stitch ? (unsigned) (int) st[i][u] : c;
+                            const double* const hb = big + (size_t) (on[i] ? b0 + i : b0) * PITCH;
+                            pc[i][u] = hb[c];
+                            ps[i][u] = hb[cs];
+                        }
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+#pragma unroll
+                        for (int u = 0; u < BATCH; ++u) {
+                            const double tot = st[i][u] >= 0.0 ? tl[i][u] + (pc[i][u] - ps[i][u]) : 0.0;  // heads of the CTAs cs + 1 .. c
                             S[i] += tot;
                             Q[i] = fma(tot, tot, Q[i]);
                         }
-                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+#pragma unroll
+                        for (int u = 0; u < BATCH; ++u) {
+                            if (st[i][u] >= 0.0) {
+                                const unsigned c = c0 + u * 32 + lane, cs = (unsigned) st[i][u];
+                                double tot = tl[i][u];
+                                for (unsigned k = cs + 1; k < c; ++k) tot += ld_cg_f64(pS[i] + 2 * SLOT + k);
+                                tot += hd[i][u];
+                                S[i] += tot;
+                                Q[i] = fma(tot, tot, Q[i]);
+                            }
+                        }
+                }
             }
         }
+        if (tr != nullptr && tid == 0 && b0 == 0) tr[16 + 8] = globaltimer_ns();  // cut items stitched
         for (int m = 16; m >= 1; m >>= 1)
 #pragma unroll
             for (int i = 0; i < NI; ++i) {

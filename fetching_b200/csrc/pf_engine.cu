@@ -631,6 +631,8 @@ static void print_trace(Engine& e) {
             (long long) (t[16] - t[0]), (long long) (t[17] - t[0]), (long long) (t[18] - t[0]));
     if (t[19]) fprintf(stderr, "[pf trace] finalize: partials staged %lld, first round of warp 0 %lld, warp 0 done %lld (ns after entering)\n",
                        (long long) (t[19] - t[16]), (long long) (t[20] - t[16]), (long long) (t[21] - t[16]));
+    if (t[22]) fprintf(stderr, "[pf trace] finalize, first round of warp 0: prefix sums %lld, records summed %lld, cut items stitched %lld (ns after entering)\n",
+                       (long long) (t[22] - t[16]), (long long) (t[23] - t[16]), (long long) (t[24] - t[16]));
     if (t[6]) fprintf(stderr, "[pf trace] mixture exponent form: %s\n", t[6] == 1 ? "factored" : "clamped distance");
     if (t[7]) fprintf(stderr, "[pf trace] resident kernel: command relayed %lld ns after CTA 0 saw it\n", (long long) (t[7] - t[0]));
     std::vector<long long> in, out;
