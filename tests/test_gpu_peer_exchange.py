@@ -150,8 +150,9 @@ def test_node_split_gather_lasso_and_boltzmann(fb):
     X, y, beta = models.blasso_dataset(6000, 100, seed=1)
     th = models.blasso_thetas(beta, 24, seed=2, scale=0.05)
     W, Xs = models.boltzmann_dataset(256, 40, seed=3)
-    for make, thetas in ((lambda: fb.FrontierEngine.blasso(X, y, item_rows=500), th),
-                         (lambda: fb.FrontierEngine.boltzmann_dense(W), Xs)):
+    for make, thetas, tol in ((lambda: fb.FrontierEngine.blasso(X, y, item_rows=500), th, 1e-12),
+                              (lambda: fb.FrontierEngine.blasso(X, y, item_rows=500, dtype=fb.F32), th, 1e-5),  # tcgen05 kernel
+                              (lambda: fb.FrontierEngine.boltzmann_dense(W), Xs, 1e-12)):
         with make() as full:
             fs, fq = full.eval_frontier(thetas)
         engs = [make() for _ in range(4)]
@@ -163,7 +164,7 @@ def test_node_split_gather_lasso_and_boltzmann(fb):
             for s, q in res:
                 # the slice of a rank runs with a different node-block count than the full frontier: same IEEE
                 # operations per node, possibly another summation order over columns / CTAs
-                assert rel(s, fs) < 1e-12 and rel(q, fq) < 1e-12
+                assert rel(s, fs) < tol and rel(q, fq) < tol
                 assert np.array_equal(s, res[0][0])
         finally:
             for e in engs:
