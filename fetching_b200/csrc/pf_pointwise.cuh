@@ -21,12 +21,18 @@ namespace pf {
 //   rows per iteration 4, A_k and B_k in registers, two partial sums      5.90 / 0.995 / 21.9
 //   rows per iteration 4, A_k re-read from shared memory per row          5.44 / 0.965
 //   ... and a single accumulation chain                                    5.35 / 0.950
-//   rows per iteration 2, A_k re-read, single chain  (the default)         5.24 / 0.927 / 19.7
+//   rows per iteration 2, A_k re-read, single chain                        5.24 / 0.927 / 19.7
 //   rows per iteration 3                                                   5.21 / 0.941 / 19.6
 //   rows per iteration 1                                                   6.67 / 0.989 / 26.0
 //   A_k and B_k both re-read (rows 2)                                      5.24 / 0.927 / 19.7
+// Second half of round 2 (another box: 5.38 for the two-row default above): the rows of an iteration walk the components
+// TOGETHER and share the A_k / B_k reads (PF_MIX_PAIR), and the per-row log is replaced by a running product (PF_MIX_PROD):
+//   two rows together, per-row logs (PF_MIX_PROD = 0)                      5.24 / 0.908
+//   per-row walk, running product (PF_MIX_PAIR = 0)                        5.12 / 0.953
+//   two rows together, running product                                     4.74 / 0.869 / 18.0
+//   four rows together (2 components x 4 rows), uniform masked tail step   4.67 / 0.861 / 17.7   (the default)
 #ifndef PF_MIX_RB
-#define PF_MIX_RB 4       // rows per iteration of the mixture loops
+#define PF_MIX_RB 4       // rows per iteration of the factored mixture loop (2 or 4 walk together; the clamped form keeps 2)
 #endif
 #ifndef PF_MIX_RELOAD
 #define PF_MIX_RELOAD 1   // factored form: 0 = theta-derived constants wherever the compiler puts them (registers),
