@@ -467,6 +467,9 @@ template <typename T>
 int dispatch_mixture(Engine& e, const PointwiseArgs& a, cudaStream_t s) {
     if (e.K == 8 && e.dim == 2) return launch_npl<MixtureModel<8, 2, T>, T>(e, a, s, true);
     if (e.K == 8 && e.dim == 8) return launch_npl<MixtureModel<8, 8, T>, T>(e, a, s, false);
+    if (e.K == 4 && e.dim == 2) return launch_npl<MixtureModel<4, 2, T>, T>(e, a, s, true);    // (K-unrolled loops: 2.3x the
+    if (e.K == 16 && e.dim == 2) return launch_npl<MixtureModel<16, 2, T>, T>(e, a, s, true);  //  run-time component loop)
+    if (e.K == 8 && e.dim == 4) return launch_npl<MixtureModel<8, 4, T>, T>(e, a, s, true);
     switch (e.dim) {
         case 1: return launch_npl<MixtureModelRT<1, T>, T>(e, a, s, true);
         case 2: return launch_npl<MixtureModelRT<2, T>, T>(e, a, s, true);

@@ -409,6 +409,9 @@ int res_configure_t(Engine& e) {
     if (e.desc.model == PF_MODEL_MIXTURE) {
         if (e.K == 8 && e.dim == 2) return res_configure<MixtureModel<8, 2, T>, void, T>(e);
         if (e.K == 8 && e.dim == 8) return res_configure<MixtureModel<8, 8, T>, void, T>(e);
+        if (e.K == 4 && e.dim == 2) return res_configure<MixtureModel<4, 2, T>, void, T>(e);
+        if (e.K == 16 && e.dim == 2) return res_configure<MixtureModel<16, 2, T>, void, T>(e);
+        if (e.K == 8 && e.dim == 4) return res_configure<MixtureModel<8, 4, T>, void, T>(e);
         switch (e.dim) {
             case 1: return res_configure<MixtureModelRT<1, T>, void, T>(e);
             case 2: return res_configure<MixtureModelRT<2, T>, void, T>(e);
