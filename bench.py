@@ -21,7 +21,7 @@ same job is run at every N (strong scaling; rows sharded contiguously at item bo
             N = 1, 2, 4, 8 can be compared with each other.
 `parity`    checks made inside this run: a window of every rank's shard against the oracle, bit-identity of the
             reduced sums across ranks, host path == device path.
-`configs`   (N = 1) one short measurement per BASELINE config C1..C4, each checked against the oracle.
+`configs`   (N = 1) one short measurement per BASELINE config C1..C4 (+ the PF_F32 lasso on tcgen05), each checked against the oracle.
 `scale_extra`, `node_split`  the multi-GPU cases where the exchange overhead shows: B = 1, lasso row shards,
             node split of the 10^6-row mixture.
 `cpu_baseline`  the oracle's C restatement of the same arithmetic ("port"; the reference's own
@@ -830,6 +830,9 @@ def main():
             for name, b, levels in (("normal1e6", 8, 20000), ("boltzmann", 64, 2000), ("mixture1e6", 8, 20000),
                                     ("blasso", 8, 2000)):
                 cfgs[name] = small_config(ctx, name, b, "f64", Ke, W, levels)
+            # the PF_F32 lasso: the tcgen05 kernel (3xTF32, operands and accumulators in TMEM) under the driver's clock
+            cfgs["blasso_f32_tcgen05"] = small_config(ctx, "blasso", 8, "f32", Ke, W, 0)
+            cfgs["blasso_f32_tcgen05_B64"] = small_config(ctx, "blasso", 64, "f32", Ke, W, 0)
             extras["configs"] = cfgs
 
     if rank == 0:
