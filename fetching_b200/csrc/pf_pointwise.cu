@@ -470,6 +470,13 @@ int dispatch_mixture(Engine& e, const PointwiseArgs& a, cudaStream_t s) {
     if (e.K == 4 && e.dim == 2) return launch_npl<MixtureModel<4, 2, T>, T>(e, a, s, true);    // (K-unrolled loops: 2.3x the
     if (e.K == 16 && e.dim == 2) return launch_npl<MixtureModel<16, 2, T>, T>(e, a, s, true);  //  run-time component loop)
     if (e.K == 8 && e.dim == 4) return launch_npl<MixtureModel<8, 4, T>, T>(e, a, s, true);
+    if (e.dim == 2) switch (e.K) {  // small two-dimensional mixtures
+        case 2: return launch_npl<MixtureModel<2, 2, T>, T>(e, a, s, true);
+        case 3: return launch_npl<MixtureModel<3, 2, T>, T>(e, a, s, true);
+        case 5: return launch_npl<MixtureModel<5, 2, T>, T>(e, a, s, true);
+        case 6: return launch_npl<MixtureModel<6, 2, T>, T>(e, a, s, true);
+        default: break;
+    }
     switch (e.dim) {
         case 1: return launch_npl<MixtureModelRT<1, T>, T>(e, a, s, true);
         case 2: return launch_npl<MixtureModelRT<2, T>, T>(e, a, s, true);

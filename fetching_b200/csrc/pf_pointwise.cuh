@@ -237,7 +237,7 @@ struct MixtureModel {
         return FACTORED ? theta_len + K : theta_len;
     }
     static constexpr bool PROD = FACTORED && (PF_MIX_PROD != 0);      // running product instead of a log per row
-    static constexpr bool PAIR = FACTORED && (PF_MIX_PAIR != 0) && (RB == 2 || RB == 4) && (K % 4 == 0) && (D % 2 == 0);
+    static constexpr bool PAIR = FACTORED && (PF_MIX_PAIR != 0) && (RB == 2 || RB == 4) && (K % 2 == 0) && (D % 2 == 0);
     static constexpr bool QUAD = PAIR && RB == 4;
     struct RowState {
         unsigned redo;  // slow_path_accumulate() key, tested once per tile
@@ -370,7 +370,7 @@ struct MixtureModel {
     }
     // two rows at once (PAIR): row sums into lpa / lpb
     static __device__ __forceinline__ void mix_sum2(const Node& nd, const CT (&xa)[D], const CT (&xb)[D], double& lpa, double& lpb) {
-        constexpr int G2 = 4;
+        constexpr int G2 = (K % 4 == 0) ? 4 : 2;  // components per group (K is even)
         lpa = 0.0;
         lpb = 0.0;
         const unsigned th_s = smem_u32(nd.th);

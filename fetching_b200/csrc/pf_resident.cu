@@ -412,6 +412,13 @@ int res_configure_t(Engine& e) {
         if (e.K == 4 && e.dim == 2) return res_configure<MixtureModel<4, 2, T>, void, T>(e);
         if (e.K == 16 && e.dim == 2) return res_configure<MixtureModel<16, 2, T>, void, T>(e);
         if (e.K == 8 && e.dim == 4) return res_configure<MixtureModel<8, 4, T>, void, T>(e);
+        if (e.dim == 2) switch (e.K) {
+            case 2: return res_configure<MixtureModel<2, 2, T>, void, T>(e);
+            case 3: return res_configure<MixtureModel<3, 2, T>, void, T>(e);
+            case 5: return res_configure<MixtureModel<5, 2, T>, void, T>(e);
+            case 6: return res_configure<MixtureModel<6, 2, T>, void, T>(e);
+            default: break;
+        }
         switch (e.dim) {
             case 1: return res_configure<MixtureModelRT<1, T>, void, T>(e);
             case 2: return res_configure<MixtureModelRT<2, T>, void, T>(e);

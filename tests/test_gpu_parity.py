@@ -173,7 +173,7 @@ def test_mixture_k8_d2_items(fb, orc, item_rows, B):
     assert rel(s, want[0]) < TOL64 and rel(q, want[1]) < TOL64
 
 
-@pytest.mark.parametrize("K,d", [(5, 3), (3, 1), (16, 4), (2, 8), (8, 8), (4, 2), (16, 2), (8, 4)])
+@pytest.mark.parametrize("K,d", [(5, 3), (3, 1), (16, 4), (2, 8), (8, 8), (4, 2), (16, 2), (8, 4), (2, 2), (3, 2), (5, 2), (6, 2)])
 def test_mixture_other_shapes(fb, orc, K, d):
     from fetching_b200 import models
     data, pos = models.mixture_dataset(30000, K, d, seed=K + d)

@@ -90,7 +90,7 @@ def test_mixture_1e6_resident(fb, orc, B):
     assert rel(s, want[0]) < TOL64 and rel(q, want[1]) < TOL64
 
 
-@pytest.mark.parametrize("shape", [(8, 2, 1000), (8, 2, 7), (8, 8, 500), (5, 3, 100), (3, 1, 64), (4, 2, 250), (16, 2, 1000), (8, 4, 500)])
+@pytest.mark.parametrize("shape", [(8, 2, 1000), (8, 2, 7), (8, 8, 500), (5, 3, 100), (3, 1, 64), (4, 2, 250), (16, 2, 1000), (8, 4, 500), (3, 2, 100), (6, 2, 333)])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_mixture_shapes_resident(fb, orc, shape, dtype):
     from fetching_b200 import models
