@@ -115,6 +115,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ double shfl_down_f64(double v, int delta) {
+    const int hi = __shfl_down_sync(0xffffffffu, __double2hiint(v), delta);
+    const int lo = __shfl_down_sync(0xffffffffu, __double2loint(v), delta);
+    return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
     const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), delta);
     const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), delta);

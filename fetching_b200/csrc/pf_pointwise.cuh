@@ -752,14 +752,28 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
 
     // ---------------------------------------------------------------------- consumer warps
     const unsigned B = a.B;
-    unsigned NB = 32;  // node lanes (power of two >= min(B, 32))
-    if (B < 32) {
-        NB = 1;
-        while (NB < B) NB <<= 1;
-    }
+    // lane = point-lane * NB + node: NB = min(B, 32) node lanes, PL = 32 / NB point lanes; when NB does not divide 32 the
+    // last 32 - PL * NB lanes are spares (they re-walk the rows of point lane 0 and their sums are dropped).  B = 3 / 5 / 6
+    // keep 30 of 32 lanes busy (a power-of-two layout: 24 / 20 / 24), B = 9 / 10: 27 / 30 (18 / 20).
+    const unsigned NB = B < 32 ? B : 32;
     const unsigned PL = 32 / NB;
-    const unsigned nb = lane & (NB - 1), pl = lane / NB;
-    const unsigned slot = warp * PL + pl, nslots = PW_CONSUMER_WARPS * PL;
+    const bool nb_pow2 = (NB & (NB - 1)) == 0;
+    const unsigned nb = lane % NB, pl = lane / NB;
+    const unsigned slot = warp * PL + (pl < PL ? pl : 0u), nslots = PW_CONSUMER_WARPS * PL;
+    // sum over the point lanes of a node (valid in the lanes pl == 0): butterfly, or a tree of strided shuffles
+    auto point_lane_sum = [&](double v) {
+        if (nb_pow2) {
+#pragma unroll
+            for (unsigned m = 16; m >= 1; m >>= 1)  // (unrolled: the run-time loop cost 10 instructions per step -- at B = 1,
+                if (m >= NB) v += shfl_xor_f64(v, m);  //  five steps per four rows of a lane; NB is warp-uniform)
+        } else {
+            for (unsigned off = 1; off < PL; off <<= 1) {
+                const double o = shfl_down_f64(v, (int) (off * NB));
+                if (pl + off < PL) v += o;
+            }
+        }
+        return v;
+    };
 
     typename M::Node nd[NPL];
     if constexpr (M::THETA_IN_SMEM) {
@@ -993,11 +1007,8 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
             double* r = red + (tt & (PW_RED_BUFS - 1)) * (PW_CONSUMER_WARPS * RS);
 #pragma unroll
             for (int n = 0; n < NPL; ++n) {
-                double v = accS[n];
+                const double v = point_lane_sum(accS[n]);
                 accS[n] = 0.0;
-#pragma unroll
-                for (unsigned m = 16; m >= 1; m >>= 1)  // (unrolled: the run-time loop cost 10 instructions per step -- at B = 1,
-                    if (m >= NB) v += shfl_xor_f64(v, m);  //  five steps per four rows of a lane; NB is warp-uniform)
                 if (pl == 0) r[warp * RS + nb + 32 * n] = v;
             }
             const int bar = PW_BAR_TILE0 + (int) (tt & (PW_RED_BUFS - 1));
@@ -1024,11 +1035,7 @@ __device__ __forceinline__ void pw_main(const A& a, const PwShared& sh) {
         // one block reduction at the very end: every row is its own item
 #pragma unroll
         for (int n = 0; n < NPL; ++n) {
-            double v = accS[n], q = accQ[n];
-            for (unsigned m = 16; m >= NB; m >>= 1) {
-                v += shfl_xor_f64(v, m);
-                q += shfl_xor_f64(q, m);
-            }
+            const double v = point_lane_sum(accS[n]), q = point_lane_sum(accQ[n]);
             if (pl == 0) {
                 red[warp * (32 * NPL) + nb + 32 * n] = v;
                 red[PW_CONSUMER_WARPS * (32 * NPL) + warp * (32 * NPL) + nb + 32 * n] = q;
