@@ -517,6 +517,42 @@ uint32_t pointwise_max_frontier(const Engine& e) {
     return 64;
 }
 
+// FP64 mixture: how a frontier of B nodes is cut into launches of <= 32 nodes.  The kernel is FP64-bound, so a launch
+// costs what its LANE LAYOUT costs -- 11 .. 16 nodes all run with two point lanes (the time of 16), 17 .. 32 with one (the
+// time of 32) -- and reading the data once more is free: 12 nodes as 8 + 4 take 7.3 ms per 1e8 rows instead of 9.1, 20 as
+// 16 + 4 11.7 instead of 17.7.  Measured ms per 1e8 rows of one launch (K = 8, d = 2; other shapes scale alike) + 12 us per
+// launch; the cheapest cut by dynamic programming.  (Engines of a multi-GPU group keep the fixed 32 + rest cut.)
+static unsigned mixture_plan(unsigned B, unsigned long long rows, unsigned (&chunk)[64]) {
+    static const double t1[33] = {0,    0.86, 1.41, 2.31, 2.55, 3.39, 3.94, 4.72, 4.72, 6.17, 6.15, 9.1,  9.1,  9.1,  9.1,  9.1, 9.1,
+                                  17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7};
+    const double scale = (double) rows / 1e8, per_launch = 0.012;
+    double cost[65];
+    unsigned first[65];
+    cost[0] = 0.0;
+    first[0] = 0;
+    for (unsigned b = 1; b <= B; ++b) {
+        cost[b] = 1e300;
+        for (unsigned c = 1; c <= 32 && c <= b; ++c) {
+            const double v = cost[b - c] + t1[c] * scale + per_launch;
+            if (v < cost[b] - 1e-12) {
+                cost[b] = v;
+                first[b] = c;
+            }
+        }
+    }
+    unsigned n = 0;
+    for (unsigned b = B; b > 0; b -= first[b]) chunk[n++] = first[b];
+    // widest launch first (deterministic order)
+    for (unsigned i = 0; i + 1 < n; ++i)
+        for (unsigned j = i + 1; j < n; ++j)
+            if (chunk[j] > chunk[i]) {
+                const unsigned t = chunk[i];
+                chunk[i] = chunk[j];
+                chunk[j] = t;
+            }
+    return n;
+}
+
 int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out, uint64_t first_item,
                      uint64_t n_items, cudaStream_t s) {
     PointwiseArgs a{};
@@ -541,14 +577,31 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     a.done_flag = e.done_flag;
     a.done_seq = e.done_seq;
     for (int j = 0; j < 8; ++j) a.xmax[j] = e.xmax[j];
+    // FP64 mixture: the frontier may be cut into several launches (mixture_plan)
+    unsigned chunk[64], n_chunks = 1;
+    chunk[0] = B;
+    const bool may_cut = e.desc.model == PF_MODEL_MIXTURE && !e.f32 && e.gather_per == 0 && B <= 64;
+    if (may_cut) {
+        // fixed cut (32 + rest) for the engines of a multi-GPU group -- their shares may be unequal and the cut must not
+        // depend on the rows -- and for data sets within the resident kernel's reach: the resident kernel scores commands
+        // of <= 32 nodes in one pass each, and the launched path reproduces its sums bit for bit
+        if (e.nranks > 1 || n_items * e.item_rows < 4000000ull) {
+            if (B > 32) {
+                n_chunks = 2;
+                chunk[0] = 32;
+                chunk[1] = B - 32;
+            }
+        } else
+            n_chunks = mixture_plan(B, n_items * e.item_rows, chunk);
+    }
     if (a.row_end <= a.row_begin) {  // no rows here: zeros (+ the same exchanges the other ranks' launches make)
-        if (e.desc.model == PF_MODEL_MIXTURE && !e.f32 && B > 32 && e.gather_per == 0) {
-            const int r1 = launch_exchange_only(e, 32, d_out, s, 0, B);
-            if (r1 < 0) return r1;
-            const int r2 = launch_exchange_only(e, B - 32, d_out, s, 32, B);
-            return r2 < 0 ? r2 : r1 + r2;
+        int total = 0;
+        for (unsigned i = 0, off = 0; i < n_chunks; off += chunk[i], ++i) {
+            const int r = n_chunks == 1 ? launch_exchange_only(e, B, d_out, s) : launch_exchange_only(e, chunk[i], d_out, s, off, B);
+            if (r < 0) return r;
+            total += r;
         }
-        return launch_exchange_only(e, B, d_out, s);
+        return total;
     }
     a.xchg = e.next_xchg();
     if (e.desc.model == PF_MODEL_NORMAL) {
@@ -559,30 +612,28 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
         const bool general = e.normal_general;
         return e.f32 ? dispatch_normal<float>(e, a, s, general) : dispatch_normal<double>(e, a, s, general);
     }
-    if (!e.f32 && B > 32 && a.xchg.gather_per == 0) {
-        // FP64 mixture, more than 32 nodes: two launches of <= 32 nodes (one node per lane) beat one launch with two
-        // nodes per lane, which runs out of registers (N = 1e8, B = 64: 45.5 vs 52.7 ms); the data set is read twice,
-        // which an FP64-bound kernel does not notice.  Each launch makes its own peer exchange.
-        PointwiseArgs lo = a, hi = a;
-        lo.B = 32;
-        lo.out_off = 0;
-        lo.out_stride = B;
-        lo.theta_inline_n = 0;
-        hi.B = B - 32;
-        hi.theta = d_theta + (size_t) 32 * e.theta_len;
-        hi.out_off = 32;
-        hi.out_stride = B;
-        hi.theta_inline_n = 0;
-        if (a.theta_inline_n) {  // (tiny thetas only) the inline copy holds all B nodes: re-slice it
-            lo.theta_inline_n = 32 * e.theta_len;
-            hi.theta_inline_n = (B - 32) * e.theta_len;
-            memcpy(hi.theta_inline, a.theta_inline + (size_t) 32 * e.theta_len, (size_t) hi.theta_inline_n * sizeof(double));
+    if (may_cut && n_chunks > 1) {
+        // several launches of <= 32 nodes (one node per lane: two per lane run out of registers -- N = 1e8, B = 64: 45.5 vs
+        // 52.7 ms); the data set is read once per launch, which an FP64-bound kernel does not notice.  Each launch makes
+        // its own peer exchange.
+        int total = 0;
+        for (unsigned i = 0, off = 0; i < n_chunks; off += chunk[i], ++i) {
+            PointwiseArgs c = a;
+            c.B = chunk[i];
+            c.theta = d_theta + (size_t) off * e.theta_len;
+            c.out_off = off;
+            c.out_stride = B;
+            c.theta_inline_n = 0;
+            if (a.theta_inline_n) {  // (tiny thetas only) the inline copy holds all B nodes: re-slice it
+                c.theta_inline_n = chunk[i] * e.theta_len;
+                memcpy(c.theta_inline, a.theta_inline + (size_t) off * e.theta_len, (size_t) c.theta_inline_n * sizeof(double));
+            }
+            if (i > 0) c.xchg = e.next_xchg();
+            const int r = dispatch_mixture<double>(e, c, s);
+            if (r < 0) return r;
+            total += r;
         }
-        const int r1 = dispatch_mixture<double>(e, lo, s);
-        if (r1 < 0) return r1;
-        hi.xchg = e.next_xchg();
-        const int r2 = dispatch_mixture<double>(e, hi, s);
-        return r2 < 0 ? r2 : r1 + r2;
+        return total;
     }
     return e.f32 ? dispatch_mixture<float>(e, a, s) : dispatch_mixture<double>(e, a, s);
 }
