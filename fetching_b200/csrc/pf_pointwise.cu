@@ -522,10 +522,10 @@ uint32_t pointwise_max_frontier(const Engine& e) {
 // time of 32) -- and reading the data once more is free: 12 nodes as 8 + 4 take 7.3 ms per 1e8 rows instead of 9.1, 20 as
 // 16 + 4 11.7 instead of 17.7.  Measured ms per 1e8 rows of one launch (K = 8, d = 2; other shapes scale alike) + 12 us per
 // launch; the cheapest cut by dynamic programming.  (Engines of a multi-GPU group keep the fixed 32 + rest cut.)
-static unsigned mixture_plan(unsigned B, unsigned long long rows, unsigned (&chunk)[64]) {
+static unsigned mixture_plan(unsigned B, unsigned long long rows, unsigned (&chunk)[64], double dtype_scale = 1.0) {
     static const double t1[33] = {0,    0.86, 1.41, 2.31, 2.55, 3.39, 3.94, 4.72, 4.72, 6.17, 6.15, 9.1,  9.1,  9.1,  9.1,  9.1, 9.1,
                                   17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7, 17.7};
-    const double scale = (double) rows / 1e8, per_launch = 0.012;
+    const double scale = (double) rows / 1e8 * dtype_scale, per_launch = 0.012;
     double cost[65];
     unsigned first[65];
     cost[0] = 0.0;
@@ -580,6 +580,12 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
     // FP64 mixture: the frontier may be cut into several launches (mixture_plan)
     unsigned chunk[64], n_chunks = 1;
     chunk[0] = B;
+    // PF_F32: the same lane layouts, 0.58x the time (12 / 16 nodes 5.08 ms per 1e8 rows, 24 / 32 9.78, and 33 .. 64 in one
+    // launch with two nodes per lane 19.6: 40 nodes as 32 + 8 take 12.5) -- cut by the same plan on large single-GPU data
+    // sets, otherwise launched as before (one launch)
+    const bool cut_f32 = e.desc.model == PF_MODEL_MIXTURE && e.f32 && e.gather_per == 0 && B <= 64 && e.nranks <= 1 &&
+                         n_items * e.item_rows >= 4000000ull;
+    if (cut_f32) n_chunks = mixture_plan(B, n_items * e.item_rows, chunk, 0.58);
     const bool may_cut = e.desc.model == PF_MODEL_MIXTURE && !e.f32 && e.gather_per == 0 && B <= 64;
     if (may_cut) {
         // fixed cut (32 + rest) for the engines of a multi-GPU group -- their shares may be unequal and the cut must not
@@ -612,7 +618,7 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
         const bool general = e.normal_general;
         return e.f32 ? dispatch_normal<float>(e, a, s, general) : dispatch_normal<double>(e, a, s, general);
     }
-    if (may_cut && n_chunks > 1) {
+    if ((may_cut || cut_f32) && n_chunks > 1) {
         // several launches of <= 32 nodes (one node per lane: two per lane run out of registers -- N = 1e8, B = 64: 45.5 vs
         // 52.7 ms); the data set is read once per launch, which an FP64-bound kernel does not notice.  Each launch makes
         // its own peer exchange.
@@ -629,7 +635,7 @@ int launch_pointwise(Engine& e, uint32_t B, const double* d_theta, double* d_out
                 memcpy(c.theta_inline, a.theta_inline + (size_t) off * e.theta_len, (size_t) c.theta_inline_n * sizeof(double));
             }
             if (i > 0) c.xchg = e.next_xchg();
-            const int r = dispatch_mixture<double>(e, c, s);
+            const int r = e.f32 ? dispatch_mixture<float>(e, c, s) : dispatch_mixture<double>(e, c, s);
             if (r < 0) return r;
             total += r;
         }
